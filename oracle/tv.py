@@ -1,0 +1,150 @@
+"""Total-variation pieces: TVnorm (periodic backward differences) and the
+Chambolle dual-projection prox with the reference's stop test.
+
+Oracle (test infrastructure).  numpy float64 restatement of
+  utils/TVnorm.m, SALSA/diffh.m, SALSA/diffv.m, SALSA/conv2c.m,
+  utils/chambolle_prox_TV_stop.m
+"""
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------
+# SALSA/conv2c.m  (literal: wrap-around padding + conv2 'valid')
+# --------------------------------------------------------------------------
+def _wraparound(x, m):
+    """SALSA/conv2c.m:7-50."""
+    mx, nx = x.shape
+    mm, nm = m.shape
+    if mm > mx or nm > nx:
+        raise ValueError("Mask does not fit inside array")      # :14-16
+    mo = (1 + mm) // 2; no = (1 + nm) // 2                      # :18
+    ml = mo - 1; nl = no - 1                                    # :19
+    mr = mm - mo; nr = nm - no                                  # :20
+    me = mx - ml + 1; ne = nx - nl + 1                          # :21
+    mt = mx + ml; nt = nx + nl                                  # :22
+    my = mx + mm - 1; ny = nx + nm - 1                          # :23
+    y = np.zeros((my, ny))
+    # 1-based inclusive MATLAB ranges a:b  ->  python slices [a-1:b]
+    y[mo - 1:mt, no - 1:nt] = x                                 # :26
+    if ml > 0:
+        y[0:ml, no - 1:nt] = x[me - 1:mx, :]                    # :28
+        if nl > 0:
+            y[0:ml, 0:nl] = x[me - 1:mx, ne - 1:nx]             # :30
+        if nr > 0:
+            y[0:ml, nt:ny] = x[me - 1:mx, 0:nr]                 # :33
+    if mr > 0:
+        y[mt:my, no - 1:nt] = x[0:mr, :]                        # :37
+        if nl > 0:
+            y[mt:my, 0:nl] = x[0:mr, ne - 1:nx]                 # :39
+        if nr > 0:
+            y[mt:my, nt:ny] = x[0:mr, 0:nr]                     # :42
+    if nl > 0:
+        y[mo - 1:mt, 0:nl] = x[:, ne - 1:nx]                    # :46
+    if nr > 0:
+        y[mo - 1:mt, nt:ny] = x[:, 0:nr]                        # :49
+    return y
+
+
+def conv2c_literal(x, h):
+    """SALSA/conv2c.m:1-4 using scipy's conv2 equivalent."""
+    from scipy.signal import convolve2d
+    h = np.atleast_2d(np.asarray(h, dtype=np.float64))
+    return convolve2d(_wraparound(np.asarray(x, dtype=np.float64), h), h, mode="valid")
+
+
+def diffh_literal(x):
+    return conv2c_literal(x, np.array([[0.0, 1.0, -1.0]]))      # diffh.m:2-3
+
+
+def diffv_literal(x):
+    return conv2c_literal(x, np.array([[0.0, 1.0, -1.0]]).T)    # diffv.m:2-3
+
+
+# Closed forms (tests check them bit-for-bit vs the literal)
+def diffh(x):
+    """x(i,j) - x(i,j-1) with periodic wrap  (SALSA/diffh.m:1-3)."""
+    return x - np.roll(x, 1, axis=1)
+
+
+def diffv(x):
+    """x(i,j) - x(i-1,j) with periodic wrap  (SALSA/diffv.m:1-3)."""
+    return x - np.roll(x, 1, axis=0)
+
+
+def TVnorm(x):
+    """utils/TVnorm.m:1-2."""
+    return float(np.sum(np.sum(np.sqrt(diffh(x) ** 2 + diffv(x) ** 2), axis=0)))
+
+
+# --------------------------------------------------------------------------
+# utils/chambolle_prox_TV_stop.m
+# --------------------------------------------------------------------------
+def DivergenceIm(p1, p2):
+    """chambolle_prox_TV_stop.m:152-159.  Last row/col is -p(end) (Q3)."""
+    z = p2[:, 1:-1] - p2[:, :-2]                                # :153
+    v = np.concatenate([p2[:, :1], z, -p2[:, -1:]], axis=1)     # :154
+    z = p1[1:-1, :] - p1[:-2, :]                                # :156
+    u = np.concatenate([p1[:1, :], z, -p1[-1:, :]], axis=0)     # :157
+    return v + u                                                # :159
+
+
+def GradientIm(u):
+    """chambolle_prox_TV_stop.m:161-166 (forward differences, zero last row/col)."""
+    z = u[1:, :] - u[:-1, :]
+    dux = np.concatenate([z, np.zeros((1, z.shape[1]))], axis=0)    # :163
+    z = u[:, 1:] - u[:, :-1]
+    duy = np.concatenate([z, np.zeros((z.shape[0], 1))], axis=1)    # :166
+    return dux, duy
+
+
+def chambolle_prox_TV_stop(g, *varargin, return_info=False):
+    """[f, px, py] = chambolle_prox_TV_stop(g, 'lambda', l, 'maxiter', K, ...)
+    utils/chambolle_prox_TV_stop.m:1-150.  Option names are case-insensitive
+    (:88).  Omitting 'maxiter' raises, like the reference's undefined `MaxIter`
+    (Q4, :80/:96/:131)."""
+    g = np.asarray(g, dtype=np.float64)
+    px = np.zeros(g.shape)                                      # :68
+    py = np.zeros(g.shape)                                      # :69
+    k = 0                                                       # :71
+    tau = 0.249; tol = 1e-3; lam = 1.0; verbose = 0             # :77-81
+    MaxIter = None                                              # (default is mis-named `maxiter`, :80)
+    for i in range(0, len(varargin) - 1, 2):                    # :87
+        name = str(varargin[i]).upper()
+        val = varargin[i + 1]
+        if name == "LAMBDA":
+            lam = float(val)
+        elif name == "VERBOSE":
+            verbose = val
+        elif name == "TOL":
+            tol = float(val)
+        elif name == "MAXITER":
+            MaxIter = int(val)
+        elif name == "TAU":
+            tau = float(val)
+        elif name == "DUALVARS":                                # :99-107
+            M, N = g.shape
+            val = np.asarray(val, dtype=np.float64)
+            Maux, Naux = val.shape
+            if M != Maux or Naux != 2 * N:
+                raise ValueError("Wrong size of the dual variables")
+            py = val[:, M:].copy()                              # :106 (splits at M: square only, Q5)
+            px = val[:, :M].copy()                              # :107
+    err = np.nan
+    while True:                                                 # :120
+        k += 1
+        divp = DivergenceIm(px, py)                             # :123
+        u = divp - g / lam                                      # :124
+        upx, upy = GradientIm(u)                                # :126
+        tmp = np.sqrt(upx ** 2 + upy ** 2)                      # :127
+        err = np.sum((-upx + tmp * px) ** 2 + (-upy + tmp * py) ** 2) ** 0.5   # :128
+        px = (px + tau * upx) / (1 + tau * tmp)                 # :129
+        py = (py + tau * upy) / (1 + tau * tmp)                 # :130
+        if MaxIter is None:
+            raise NameError("Undefined function or variable 'MaxIter'")  # Q4
+        if not ((k < MaxIter) and (err > tol)):                 # :131
+            break
+    f = g - lam * DivergenceIm(px, py)                          # :149
+    if return_info:
+        return f, px, py, k, float(err)
+    return f, px, py
