@@ -1,0 +1,126 @@
+// psf.cuh - parametric PSF taps, their parameter derivatives and the
+// on-the-fly spectrum  H[k,q] = sum_{i,j<t} h[i,j] e^{-2 pi i k i/nx} e^{-2 pi i q j/ny}
+// which is what utils/resize.m:1-12 (pad at the top-left corner + fft2) yields.
+//
+// Reference formulas restated here:
+//   utils/Gaussian_psf.m:2-19, utils/Sum_gauss_psf.m:1-28, utils/diff_fftgaus_w1.m:2-26, w2.m:2-26
+//   utils/moffat_psf.m:2-23,   utils/sum_mof_psf.m:1-40,   utils/diff_moffat_alpha.m:1-22, beta.m:1-23
+//   utils/laplace_psf.m:1-15,  utils/sum_lap_psf.m:1-28,   utils/diff_laplace_b.m:1-19
+#pragma once
+#include "common.cuh"
+
+namespace sbd {
+
+// One block (>= t*t threads, blockDim <= 256).  taps layout: [m][j*t + i],
+// m = 0 PSF, 1 d/dpsi0, 2 d/dpsi1;  i = row (fast axis), j = column.
+// `sm` : 3*MAXT*MAXT + 3 doubles of shared memory.
+__device__ __forceinline__ void psf_taps_block(int model, int t, double phi, double p0, double p1,
+                                               double* __restrict__ taps, double* sm) {
+    const int e = threadIdx.x, tt = t * t;
+    double f = 0.0, d0 = 0.0, d1 = 0.0;
+    if (e < tt) {
+        const int i = e % t, j = e / t;
+        const double half = 0.5 * (double)(t - 1);
+        const double xi = (double)i - half;         // row coordinate   (v in Gaussian_psf.m:9)
+        const double xj = (double)j - half;         // column coordinate (u)
+        const double twopi = 6.283185307179586476925286766559;
+        if (model == SBD_GAUSSIAN) {
+            const double w1 = p0, w2 = p1;
+            double sn, cs;
+            sincos(phi, &sn, &cs);
+            const double U = xj * cs - xi * sn;     // Gaussian_psf.m:11
+            const double V = xj * sn + xi * cs;     // :12
+            const double c = w1 * w1 * (U * U) + w2 * w2 * (V * V);    // :14
+            const double ex = exp(-c / 2.0);
+            f = ((w1 * w2) / twopi) * ex;                               // :16
+            d0 = (w2 / twopi) * (1.0 - w1 * w1 * (U * U)) * ex;         // Sum_gauss_psf.m:22
+            d1 = (w1 / twopi) * (1.0 - w2 * w2 * (V * V)) * ex;         // Sum_gauss_psf.m:20
+        } else if (model == SBD_MOFFAT) {
+            const double a = p0, b = p1, b2 = b + 2.0;
+            const double xy = xi * xi + xj * xj;                        // moffat_psf.m:15
+            const double a2 = a * a;
+            const double base = xy * a2 / b + 1.0;
+            const double pw = pow(base, -b2 / 2.0);
+            f = a2 * pw / twopi;                                        // moffat_psf.m:16
+            // diff_moffat_alpha.m:17 - the stray 2 in the denominator is the reference's (Q7)
+            d0 = (2.0 - ((b2 * xy * a2) / (2.0 * (b + xy * a2)))) * pw * (a / twopi);
+            // diff_moffat_beta.m:17-18
+            d1 = (-log(base) + (b2 * xy * a2) / (b * (b + xy * a2))) * pw * (a2 / (2.0 * twopi));
+        } else {
+            const double b = p0;
+            const double s = fabs(xi) + fabs(xj);
+            const double ex = exp(-b * s);
+            f = (b * b / 4.0) * ex;                                     // laplace_psf.m:8
+            d0 = ((2.0 * b - b * b * s) / 4.0) * ex;                    // diff_laplace_b.m:10-12
+            d1 = 0.0;
+        }
+        sm[e] = f; sm[MAXT * MAXT + e] = d0; sm[2 * MAXT * MAXT + e] = d1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {                           // sequential sums (fixed order)
+        double s = 0.0;
+        const double* p = sm + threadIdx.x * MAXT * MAXT;
+        for (int q = 0; q < tt; ++q) s += p[q];
+        sm[3 * MAXT * MAXT + threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (e < tt) {
+        const double S = sm[3 * MAXT * MAXT], S0 = sm[3 * MAXT * MAXT + 1], S1 = sm[3 * MAXT * MAXT + 2];
+        taps[e] = f / S;                                                // Gaussian_psf.m:18
+        taps[tt + e] = (d0 * S - f * S0) / (S * S);                     // diff_fftgaus_w1.m:24
+        taps[2 * tt + e] = (d1 * S - f * S1) / (S * S);
+    }
+}
+
+__global__ void k_psf_taps(int model, int t, double phi, const Control* __restrict__ ctl,
+                           const double* __restrict__ psi_override, double* __restrict__ taps) {
+    __shared__ double sm[3 * MAXT * MAXT + 3];
+    const double p0 = psi_override ? psi_override[0] : ctl->psi[0];
+    const double p1 = psi_override ? psi_override[1] : ctl->psi[1];
+    psf_taps_block(model, t, phi, p0, p1, taps, sm);
+}
+
+// coef[m][k][j] = sum_i taps[m][j*t+i] * W_nx^{k i},  k < nk, j < t.
+// One thread per (m,k,j).  tw_nx[n] = exp(-2 pi i n / nx).
+__global__ void k_psf_colcoef(int t, int nx, int nk, const double* __restrict__ taps,
+                              const double2* __restrict__ tw_nx, double2* __restrict__ coef) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = 3 * nk * t;
+    if (idx >= total) return;
+    const int j = idx % t, k = (idx / t) % nk, m = idx / (t * nk);
+    const double* h = taps + (size_t)m * t * t + (size_t)j * t;
+    double re = 0.0, im = 0.0;
+    for (int i = 0; i < t; ++i) {
+        const double2 w = tw_nx[(int)(((long long)k * i) & (nx - 1))];
+        re = fma(h[i], w.x, re);
+        im = fma(h[i], w.y, im);
+    }
+    coef[((size_t)m * nk + k) * MAXT + j] = make_double2(re, im);
+}
+
+// Horner evaluation of sum_j a[j] w^j
+__device__ __forceinline__ double2 psf_horner(const double2* __restrict__ a, int t, double2 w) {
+    double2 acc = a[t - 1];
+    for (int j = t - 2; j >= 0; --j) acc = cfma(acc, w, a[j]);
+    return acc;
+}
+
+// Full rows x cols spectrum for sbd_psf_spectrum (API / parity path only).
+// coef was built with nk = nx.  Output column-major: element (k,q) at q*nx+k.
+__global__ void k_psf_spectrum(int t, int nx, int ny, int m, const double2* __restrict__ coef,
+                               const double2* __restrict__ tw_ny, double* __restrict__ re,
+                               double* __restrict__ im) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)nx * ny) return;
+    const int k = (int)(idx % nx), q = (int)(idx / nx);
+    const double2* a = coef + ((size_t)m * nx + k) * MAXT;
+    double sr = 0.0, si = 0.0;
+    for (int j = 0; j < t; ++j) {
+        const double2 w = tw_ny[(int)(((long long)q * j) & (ny - 1))];
+        const double2 p = cmul(a[j], w);
+        sr += p.x; si += p.y;
+    }
+    re[idx] = sr; im[idx] = si;
+}
+
+}  // namespace sbd

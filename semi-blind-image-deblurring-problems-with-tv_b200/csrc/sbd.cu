@@ -1,0 +1,1017 @@
+// sbd.cu - libsbd.so: context, launch logic and the C ABI of include/sbd.h.
+// Hand-written CUDA for sm_100a, fp64.  No CPU fallback anywhere in this file:
+// every numerical result is produced by the kernels in tv.cuh / fft.cuh /
+// sapg.cuh / psf.cuh; the host code only sequences launches and post-processes
+// scalar trajectories (running means, Guassian.m:218-247).
+#include "common.cuh"
+#include "philox.cuh"
+#include "psf.cuh"
+#include "tv.cuh"
+#include "fft.cuh"
+#include "sapg.cuh"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+using namespace sbd;
+
+// ---------------------------------------------------------------------------
+// NCCL through dlopen (keeps libsbd.so loadable without NCCL; multi-GPU calls
+// fail loudly with SBD_E_COMM if it cannot be found).
+// ---------------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) return false;
+        GetUniqueId = (int (*)(nccl_uid*))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (int (*)(nccl_comm))dlsym(h, "ncclCommDestroy");
+        AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm, cudaStream_t))dlsym(h, "ncclAllGather");
+        GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllGather;
+    }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8;     // ncclDouble
+std::string g_create_error;
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct sbd_ctx {
+    int device = 0;
+    int nx = 0, ny = 0;             // rows (fast) / cols (slow)
+    int t = 7, model = 0;
+    double phi = 0.0;
+    int max_batch = 1;
+    bool pow2 = false;
+    size_t npix = 0;
+    int sp = 0, nk = 0;             // half-spectrum pitch / number of bins (nx/2+1)
+    size_t spec_elems = 0;          // per image, in double2
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    std::string err;
+
+    // geometry
+    int tvV = 1, tv_gx = 1, tv_gy = 1, tv_seg = 8, tv_parts = 1;
+    int rowsLP = 1, rowsT = 32, colsC = 2, colsT = 32, ntiles = 1;
+    int geom_batch = -1;
+
+    // device buffers
+    double2 *tw_nx = nullptr, *tw_ny = nullptr;
+    double* taps = nullptr;         // [3][t*t]
+    double2* coef = nullptr;        // [3][nx][MAXT]
+    Control* ctl = nullptr;
+    ChambState* chst = nullptr;
+    unsigned int *cnt_tv = nullptr, *cnt_col = nullptr, *cnt_sq = nullptr;
+    double *stats = nullptr, *allstats = nullptr;
+    double *part_tv = nullptr, *part_ch = nullptr, *part_col = nullptr, *part_sq = nullptr;
+    double* psi_dev = nullptr;      // [2] override for operator calls
+    // workspaces (sized for ws_batch images)
+    int ws_batch = 0;
+    double *X = nullptr, *P = nullptr, *Gf = nullptr, *px0 = nullptr, *py0 = nullptr, *px1 = nullptr, *py1 = nullptr;
+    double2 *S1 = nullptr, *S2 = nullptr, *yhat = nullptr;
+    double *ximg = nullptr;         // 1-image staging (y, x_true)
+    double *post = nullptr;
+    int post_batch = 0;
+
+    // comm
+    nccl_comm comm = nullptr;
+    int nranks = 1, rank = 0;
+
+    // profiling
+    bool profile = false;
+    double phase_ms[SBD_N_PHASES] = {0};
+    long long phase_calls[SBD_N_PHASES] = {0};
+    bool phase_main_only = true;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_phase;
+};
+
+namespace {
+
+const char* kPhaseNames[SBD_N_PHASES] = {"spectral_inverse", "langevin", "chambolle_sweeps", "chambolle_other",
+                                         "tvnorm", "spectral_forward", "scalar_update", "allgather"};
+
+template <typename T>
+T* dalloc(size_t n) {
+    T* p = nullptr;
+    SBD_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+template <typename T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+void make_twiddles(int n, double2* d, cudaStream_t s) {
+    std::vector<double2> h(n);
+    for (int m = 0; m < n; ++m) {
+        // exact octant symmetry keeps e.g. W^(n/4) = -i exactly
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)n;
+        h[m].x = (double)cosl(a);
+        h[m].y = (double)sinl(a);
+    }
+    if (n >= 4) { h[n / 4] = make_double2(0.0, -1.0); h[n / 2] = make_double2(-1.0, 0.0); h[3 * n / 4] = make_double2(0.0, 1.0); }
+    else if (n == 2) h[1] = make_double2(-1.0, 0.0);
+    SBD_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, s));
+    SBD_CUDA(cudaStreamSynchronize(s));
+}
+
+void free_ws(sbd_ctx* c) {
+    dfree(c->X); dfree(c->P); dfree(c->Gf); dfree(c->px0); dfree(c->py0); dfree(c->px1); dfree(c->py1);
+    dfree(c->S1); dfree(c->S2);
+    dfree(c->chst); dfree(c->cnt_tv); dfree(c->cnt_col); dfree(c->cnt_sq); dfree(c->stats);
+    dfree(c->part_tv); dfree(c->part_ch); dfree(c->part_col); dfree(c->part_sq);
+    c->ws_batch = 0;
+}
+
+// choose launch geometry for a batch of `batch` images
+void set_geometry(sbd_ctx* c, int batch) {
+    if (c->geom_batch == batch) return;
+    const int nx = c->nx, ny = c->ny;
+    c->tvV = (nx % 2 == 0 && nx >= 64) ? 2 : 1;
+    const int strips = (nx + 32 * c->tvV - 1) / (32 * c->tvV);
+    c->tv_gx = (strips + TV_WARPS - 1) / TV_WARPS;
+    int seg = 64;
+    while (seg > 8 && (long long)c->tv_gx * ((ny + seg - 1) / seg) * batch < 4 * 148) seg /= 2;
+    if (const char* e = getenv("SBD_TV_SEG")) seg = std::max(1, atoi(e));
+    c->tv_seg = seg;
+    c->tv_gy = (ny + seg - 1) / seg;
+    c->tv_parts = c->tv_gx * c->tv_gy;
+    if (c->pow2) {
+        int LP = std::max(1, 4096 / nx);
+        LP = std::min(LP, ny / 2);
+        while (LP > 1 && (long long)(ny / 2 / LP) * batch < 2 * 148) LP /= 2;
+        c->rowsLP = LP;
+        c->rowsT = std::max(32, LP * nx / (4 * FFT_ITER));
+        int C = 8;
+        const size_t cap = (ny >= 2048) ? 128 * 1024 : 64 * 1024;
+        while (C > 2 && (size_t)C * ny * 16 > cap) C /= 2;
+        if (const char* e = getenv("SBD_COLS_C")) C = std::max(1, std::min(8, atoi(e)));
+        while (C > 1 && ((size_t)C * ny / (4 * FFT_ITER) > 1024 || (size_t)C * ny * 16 > 200 * 1024)) C /= 2;
+        c->colsC = C;
+        c->colsT = std::max(32, C * ny / (4 * FFT_ITER));
+        c->ntiles = (c->nk + C - 1) / C;
+    }
+    c->geom_batch = batch;
+}
+
+void ensure_ws(sbd_ctx* c, int batch) {
+    if (batch <= c->ws_batch) { set_geometry(c, batch); return; }
+    free_ws(c);
+    const size_t n = (size_t)batch * c->npix;
+    c->X = dalloc<double>(n); c->P = dalloc<double>(n); c->Gf = dalloc<double>(n);
+    c->px0 = dalloc<double>(n); c->py0 = dalloc<double>(n); c->px1 = dalloc<double>(n); c->py1 = dalloc<double>(n);
+    if (c->pow2) {
+        c->S1 = dalloc<double2>((size_t)batch * c->spec_elems);
+        c->S2 = dalloc<double2>((size_t)batch * c->spec_elems);
+    }
+    c->chst = dalloc<ChambState>(batch);
+    c->cnt_tv = dalloc<unsigned int>(batch); c->cnt_col = dalloc<unsigned int>(batch); c->cnt_sq = dalloc<unsigned int>(batch);
+    c->stats = dalloc<double>((size_t)batch * NSTAT);
+    SBD_CUDA(cudaMemsetAsync(c->cnt_tv, 0, sizeof(unsigned int) * batch, c->stream));
+    SBD_CUDA(cudaMemsetAsync(c->cnt_col, 0, sizeof(unsigned int) * batch, c->stream));
+    SBD_CUDA(cudaMemsetAsync(c->cnt_sq, 0, sizeof(unsigned int) * batch, c->stream));
+    SBD_CUDA(cudaMemsetAsync(c->stats, 0, sizeof(double) * batch * NSTAT, c->stream));
+    SBD_CUDA(cudaMemsetAsync(c->chst, 0, sizeof(ChambState) * batch, c->stream));
+    // partial buffers sized for the finest geometry (seg = 1 worst case is never used; seg >= 1)
+    c->geom_batch = -1;
+    set_geometry(c, batch);
+    const int strips = (c->nx + 31) / 32;
+    const size_t maxparts = (size_t)((strips + TV_WARPS - 1) / TV_WARPS) * c->ny;    // seg = 1 bound
+    c->part_tv = dalloc<double>((size_t)batch * maxparts);
+    c->part_ch = dalloc<double>((size_t)batch * maxparts);
+    c->part_col = dalloc<double>((size_t)batch * (c->nk + 1) * 4);
+    c->part_sq = dalloc<double>((size_t)batch * 1024);
+    c->ws_batch = batch;
+}
+
+// Phase timing without perturbing the run: event pairs are only RECORDED while
+// the iteration is being enqueued and resolved after the run has finished.
+struct PhaseTimer {
+    sbd_ctx* c; int phase; cudaEvent_t a = nullptr, b = nullptr;
+    PhaseTimer(sbd_ctx* c_, int p) : c(c_), phase(p) {
+        if (!c->profile) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+    ~PhaseTimer() {
+        if (!c->profile) return;
+        cudaEventRecord(b, c->stream);
+        c->ev.push_back(a); c->ev.push_back(b); c->ev_phase.push_back(phase);
+    }
+};
+
+void resolve_phase_events(sbd_ctx* c) {
+    for (size_t i = 0; i < c->ev_phase.size(); ++i) {
+        float ms = 0.f;
+        cudaEventSynchronize(c->ev[2 * i + 1]);
+        cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]);
+        c->phase_ms[c->ev_phase[i]] += ms;
+        c->phase_calls[c->ev_phase[i]] += 1;
+        cudaEventDestroy(c->ev[2 * i]); cudaEventDestroy(c->ev[2 * i + 1]);
+    }
+    c->ev.clear(); c->ev_phase.clear();
+}
+
+// ---- launch helpers --------------------------------------------------------
+#define LAUNCH_CHECK(c) do { (c)->launches++; SBD_CUDA(cudaGetLastError()); } while (0)
+
+void tvnorm(sbd_ctx* c, const double* x, double* out, int out_stride, int batch) {
+    dim3 g(c->tv_gx, c->tv_gy, batch);
+    if (c->tvV == 2)
+        k_tvnorm<2><<<g, TV_THREADS, 0, c->stream>>>(x, c->nx, c->ny, c->tv_seg, c->npix, c->part_tv, c->cnt_tv, out, out_stride);
+    else
+        k_tvnorm<1><<<g, TV_THREADS, 0, c->stream>>>(x, c->nx, c->ny, c->tv_seg, c->npix, c->part_tv, c->cnt_tv, out, out_stride);
+    LAUNCH_CHECK(c);
+}
+
+// prox with the options stored in ctl (prox_lambda_theta, tau, tol, maxiter).
+// `maxiter` is the host copy used to size the launch sequence.  The dual pair
+// starts from px0/py0 (caller zeroes or fills them).
+void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter) {
+    k_chamb_reset<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->chst, batch);
+    LAUNCH_CHECK(c);
+    dim3 grid(c->tv_gx, c->tv_gy, batch);
+    PhaseTimer* pt = new PhaseTimer(c, 2);
+    for (int s = 0; s < maxiter; ++s) {
+        const double* pxi = (s & 1) ? c->px1 : c->px0;
+        const double* pyi = (s & 1) ? c->py1 : c->py0;
+        double* pxo = (s & 1) ? c->px0 : c->px1;
+        double* pyo = (s & 1) ? c->py0 : c->py1;
+        if (c->tvV == 2)
+            k_chamb_sweep<2><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst, c->part_ch);
+        else
+            k_chamb_sweep<1><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst, c->part_ch);
+        LAUNCH_CHECK(c);
+    }
+    delete pt;
+    if (c->tvV == 2)
+        k_chamb_out<2><<<grid, TV_THREADS, 0, c->stream>>>(g, c->px0, c->py0, c->px1, c->py1, f, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst);
+    else
+        k_chamb_out<1><<<grid, TV_THREADS, 0, c->stream>>>(g, c->px0, c->py0, c->px1, c->py1, f, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst);
+    LAUNCH_CHECK(c);
+}
+
+void zero_duals(sbd_ctx* c, int batch) {
+    SBD_CUDA(cudaMemsetAsync(c->px0, 0, sizeof(double) * batch * c->npix, c->stream));
+    SBD_CUDA(cudaMemsetAsync(c->py0, 0, sizeof(double) * batch * c->npix, c->stream));
+}
+
+template <typename K>
+void set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        SBD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+#define SBD_FFT_SIZES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
+
+void rows_fwd(sbd_ctx* c, const double* x, double2* spec, int batch) {
+    const size_t smem = (size_t)c->rowsLP * c->nx * sizeof(double2);
+    dim3 g(c->ny / 2 / c->rowsLP, batch);
+    switch (c->nx) {
+#define X(N) case N: set_smem(k_rows_fwd<N>, smem); \
+        k_rows_fwd<N><<<g, c->rowsT, smem, c->stream>>>(x, spec, c->sp, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
+        SBD_FFT_SIZES(X)
+#undef X
+        default: throw Error{SBD_E_UNSUPPORTED, "rows_fwd: unsupported size"};
+    }
+    LAUNCH_CHECK(c);
+}
+
+void rows_inv(sbd_ctx* c, const double2* spec, double* out, int batch) {
+    const size_t smem = (size_t)c->rowsLP * c->nx * sizeof(double2);
+    dim3 g(c->ny / 2 / c->rowsLP, batch);
+    switch (c->nx) {
+#define X(N) case N: set_smem(k_rows_inv<N>, smem); \
+        k_rows_inv<N><<<g, c->rowsT, smem, c->stream>>>(spec, out, c->sp, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
+        SBD_FFT_SIZES(X)
+#undef X
+        default: throw Error{SBD_E_UNSUPPORTED, "rows_inv: unsupported size"};
+    }
+    LAUNCH_CHECK(c);
+}
+
+template <int MODE>
+void cols(sbd_ctx* c, const double2* in, double2* out, int batch, int opsel = 0) {
+    ColArgs a;
+    a.in = in; a.out = out; a.yhat = c->yhat; a.coef = c->coef; a.tw = c->tw_ny; a.ctl = c->ctl;
+    a.partials = c->part_col; a.counters = c->cnt_col; a.stats = c->stats;
+    a.spec_stride = c->spec_elems; a.sp = c->sp; a.nk = c->nk; a.nxfull = c->nx; a.t = c->t;
+    a.npsi = (c->model == SBD_LAPLACE) ? 1 : 2; a.C = c->colsC; a.opsel = opsel;
+    a.opscale = 1.0 / ((double)c->nx * (double)c->ny);
+    const size_t smem = (size_t)c->colsC * c->ny * sizeof(double2);
+    dim3 g(c->ntiles, batch);
+    switch (c->ny) {
+#define X(N) case N: set_smem(k_cols<N, MODE>, smem); \
+        k_cols<N, MODE><<<g, c->colsT, smem, c->stream>>>(a); break;
+        SBD_FFT_SIZES(X)
+#undef X
+        default: throw Error{SBD_E_UNSUPPORTED, "cols: unsupported size"};
+    }
+    LAUNCH_CHECK(c);
+}
+
+// PSF taps (from ctl->psi or an override on device) + column coefficients for nkc bins
+void psf_refresh_coef(sbd_ctx* c, int nkc) {
+    const int total = 3 * nkc * c->t;
+    k_psf_colcoef<<<(total + 127) / 128, 128, 0, c->stream>>>(c->t, c->nx, nkc, c->taps, c->tw_nx, c->coef);
+    LAUNCH_CHECK(c);
+}
+void psf_from_host(sbd_ctx* c, const double psi[2], int nkc) {
+    SBD_CUDA(cudaMemcpyAsync(c->psi_dev, psi, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_psf_taps<<<1, 256, 0, c->stream>>>(c->model, c->t, c->phi, c->ctl, c->psi_dev, c->taps);
+    LAUNCH_CHECK(c);
+    if (nkc > 0) psf_refresh_coef(c, nkc);
+}
+
+void require_pow2(sbd_ctx* c) {
+    SBD_REQUIRE(c->pow2, SBD_E_UNSUPPORTED,
+                "FFT operators need rows and cols to be powers of two in [16, 4096]");
+}
+
+int fail(sbd_ctx* c, const Error& e) {
+    if (c) c->err = e.msg; else g_create_error = e.msg;
+    return e.code;
+}
+
+}  // namespace
+
+#define SBD_TRY(ctx) try {
+#define SBD_CATCH(ctx)                                                     \
+    } catch (const Error& e) { return fail((ctx), e); }                    \
+      catch (const std::exception& e) { return fail((ctx), Error{SBD_E_INVALID, e.what()}); } \
+    return SBD_OK;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int sbd_version(void) { return SBD_VERSION; }
+
+const char* sbd_last_error(const sbd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+long long sbd_launch_count(const sbd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+const char* sbd_phase_name(int i) { return (i >= 0 && i < SBD_N_PHASES) ? kPhaseNames[i] : ""; }
+
+int sbd_phase_times(const sbd_ctx* ctx, double ms[SBD_N_PHASES], long long calls[SBD_N_PHASES]) {
+    if (!ctx || !ms) return SBD_E_INVALID;
+    for (int i = 0; i < SBD_N_PHASES; ++i) {
+        ms[i] = ctx->phase_ms[i];
+        if (calls) calls[i] = ctx->phase_calls[i];
+    }
+    return SBD_OK;
+}
+
+int sbd_set_profile(sbd_ctx* ctx, int on) {
+    if (!ctx) return SBD_E_INVALID;
+    ctx->profile = on != 0;
+    return SBD_OK;
+}
+
+int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, double phi,
+               int max_batch, int device) {
+    sbd_ctx* c = nullptr;
+    try {
+        SBD_REQUIRE(out, SBD_E_INVALID, "sbd_create: out is NULL");
+        *out = nullptr;
+        SBD_REQUIRE(rows >= 2 && cols >= 2, SBD_E_INVALID, "sbd_create: rows and cols must be >= 2");
+        SBD_REQUIRE(psf_size >= 1 && psf_size <= MAXT, SBD_E_INVALID, "sbd_create: psf_size must be in [1,15]");
+        SBD_REQUIRE(psf_size <= rows && psf_size <= cols, SBD_E_INVALID, "sbd_create: PSF larger than the image");
+        SBD_REQUIRE(model >= 0 && model <= 2, SBD_E_INVALID, "sbd_create: unknown PSF model");
+        SBD_REQUIRE(max_batch >= 1, SBD_E_INVALID, "sbd_create: max_batch must be >= 1");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error{SBD_E_NODEVICE, std::string("sbd_create: no CUDA device (") + cudaGetErrorString(e) +
+                                         "); libsbd has no CPU fallback"};
+        SBD_REQUIRE(device >= 0 && device < ndev, SBD_E_INVALID, "sbd_create: bad device index");
+        SBD_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        SBD_CUDA(cudaGetDeviceProperties(&prop, device));
+        SBD_REQUIRE(prop.major == 10, SBD_E_NODEVICE,
+                    "sbd_create: libsbd is built for sm_100a (Blackwell B200) only");
+        c = new sbd_ctx();
+        c->device = device; c->nx = rows; c->ny = cols; c->t = psf_size; c->model = model; c->phi = phi;
+        c->max_batch = max_batch;
+        c->npix = (size_t)rows * cols;
+        c->pow2 = is_pow2(rows) && is_pow2(cols) && rows >= 16 && cols >= 16 && rows <= 4096 && cols <= 4096;
+        c->nk = rows / 2 + 1;
+        c->sp = (c->nk + 7) / 8 * 8;
+        c->spec_elems = (size_t)c->sp * cols;
+        c->profile = getenv("SBD_PROFILE") && atoi(getenv("SBD_PROFILE")) != 0;
+        SBD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->taps = dalloc<double>(3 * MAXT * MAXT);
+        c->ctl = dalloc<Control>(1);
+        c->psi_dev = dalloc<double>(2);
+        c->ximg = dalloc<double>(c->npix);
+        SBD_CUDA(cudaMemsetAsync(c->ctl, 0, sizeof(Control), c->stream));
+        if (c->pow2) {
+            c->tw_nx = dalloc<double2>(rows); c->tw_ny = dalloc<double2>(cols);
+            make_twiddles(rows, c->tw_nx, c->stream);
+            make_twiddles(cols, c->tw_ny, c->stream);
+            c->coef = dalloc<double2>((size_t)3 * rows * MAXT);
+            c->yhat = dalloc<double2>(c->spec_elems);
+        }
+        SBD_CUDA(cudaStreamSynchronize(c->stream));
+        *out = c;
+        return SBD_OK;
+    } catch (const Error& e) {
+        if (c) { sbd_destroy(c); }
+        return fail(nullptr, e);
+    }
+}
+
+int sbd_destroy(sbd_ctx* c) {
+    if (!c) return SBD_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    free_ws(c);
+    dfree(c->tw_nx); dfree(c->tw_ny); dfree(c->taps); dfree(c->coef); dfree(c->ctl); dfree(c->psi_dev);
+    dfree(c->ximg); dfree(c->yhat); dfree(c->allstats); dfree(c->post);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SBD_OK;
+}
+
+int sbd_synchronize(sbd_ctx* c) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_CUDA(cudaSetDevice(c->device));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    SBD_CATCH(c)
+}
+
+// ---------------------------------------------------------------- PSF
+int sbd_psf_taps(sbd_ctx* c, const double psi[2], int which, double* out) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(psi && out && which >= 0 && which <= 2, SBD_E_INVALID, "sbd_psf_taps: bad argument");
+    SBD_CUDA(cudaSetDevice(c->device));
+    psf_from_host(c, psi, 0);
+    SBD_CUDA(cudaMemcpyAsync(out, c->taps + (size_t)which * c->t * c->t, sizeof(double) * c->t * c->t,
+                             cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    SBD_CATCH(c)
+}
+
+int sbd_psf_spectrum(sbd_ctx* c, const double psi[2], int which, double* re, double* im) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(psi && re && im && which >= 0 && which <= 2, SBD_E_INVALID, "sbd_psf_spectrum: bad argument");
+    require_pow2(c);
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, 1);
+    psf_from_host(c, psi, c->nx);
+    double* dre = c->X; double* dim_ = c->P;
+    k_psf_spectrum<<<(unsigned)((c->npix + 255) / 256), 256, 0, c->stream>>>(c->t, c->nx, c->ny, which, c->coef, c->tw_ny, dre, dim_);
+    LAUNCH_CHECK(c);
+    SBD_CUDA(cudaMemcpyAsync(re, dre, sizeof(double) * c->npix, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaMemcpyAsync(im, dim_, sizeof(double) * c->npix, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    SBD_CATCH(c)
+}
+
+// ---------------------------------------------------------------- blur
+int sbd_blur_dev(sbd_ctx* c, const double* d_x, const double psi[2], int op, double* d_out, int batch) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(d_x && d_out && psi && op >= 0 && op <= 3 && batch >= 1, SBD_E_INVALID, "sbd_blur: bad argument");
+    SBD_REQUIRE(batch <= c->max_batch, SBD_E_INVALID, "sbd_blur: batch exceeds max_batch");
+    SBD_REQUIRE(!(op == SBD_OP_D1 && c->model == SBD_LAPLACE), SBD_E_INVALID, "sbd_blur: Laplace PSF has one parameter");
+    require_pow2(c);
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, batch);
+    psf_from_host(c, psi, c->nk);
+    rows_fwd(c, d_x, c->S1, batch);
+    cols<COL_OP>(c, c->S1, c->S1, batch, op);
+    rows_inv(c, c->S1, d_out, batch);
+    SBD_CATCH(c)
+}
+
+int sbd_blur(sbd_ctx* c, const double* x, const double psi[2], int op, double* out, int batch) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(x && out && batch >= 1 && batch <= c->max_batch, SBD_E_INVALID, "sbd_blur: bad argument");
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, batch);
+    const size_t bytes = sizeof(double) * batch * c->npix;
+    SBD_CUDA(cudaMemcpyAsync(c->X, x, bytes, cudaMemcpyHostToDevice, c->stream));
+    int rc = sbd_blur_dev(c, c->X, psi, op, c->Gf, batch);
+    if (rc) return rc;
+    SBD_CUDA(cudaMemcpyAsync(out, c->Gf, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    SBD_CATCH(c)
+}
+
+// ---------------------------------------------------------------- TV
+int sbd_tvnorm(sbd_ctx* c, const double* x, double* out, int batch) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(x && out && batch >= 1 && batch <= c->max_batch, SBD_E_INVALID, "sbd_tvnorm: bad argument");
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, batch);
+    SBD_CUDA(cudaMemcpyAsync(c->X, x, sizeof(double) * batch * c->npix, cudaMemcpyHostToDevice, c->stream));
+    tvnorm(c, c->X, c->stats, NSTAT, batch);
+    std::vector<double> h((size_t)batch * NSTAT);
+    SBD_CUDA(cudaMemcpyAsync(h.data(), c->stats, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < batch; ++b) out[b] = h[(size_t)b * NSTAT];
+    SBD_CATCH(c)
+}
+
+int sbd_diff(sbd_ctx* c, const double* x, int axis, double* out, int batch) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(x && out && (axis == 0 || axis == 1) && batch >= 1 && batch <= c->max_batch, SBD_E_INVALID, "sbd_diff: bad argument");
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, batch);
+    const size_t n = (size_t)batch * c->npix;
+    SBD_CUDA(cudaMemcpyAsync(c->X, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    k_diff<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->X, c->P, c->nx, c->ny, axis, n);
+    LAUNCH_CHECK(c);
+    SBD_CUDA(cudaMemcpyAsync(out, c->P, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    SBD_CATCH(c)
+}
+
+static void set_chamb_options(sbd_ctx* c, double lambda, int maxiter, double tol, double tau) {
+    Control h;
+    SBD_CUDA(cudaMemcpyAsync(&h, c->ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    h.prox_lambda_theta = lambda; h.maxiter = maxiter; h.tol = tol; h.tau = tau;
+    SBD_CUDA(cudaMemcpyAsync(c->ctl, &h, sizeof(Control), cudaMemcpyHostToDevice, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+static void fetch_chamb_state(sbd_ctx* c, int batch, int* iters, double* err) {
+    if (!iters && !err) return;
+    std::vector<ChambState> h(batch);
+    SBD_CUDA(cudaMemcpyAsync(h.data(), c->chst, sizeof(ChambState) * batch, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < batch; ++b) {
+        if (iters) iters[b] = h[b].k;
+        if (err) err[b] = h[b].err;
+    }
+}
+
+int sbd_tvprox_dev(sbd_ctx* c, const double* d_g, double lambda, int maxiter, double tol, double tau,
+                   double* d_f, int* iters, double* err, int batch) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(d_g && d_f && batch >= 1 && batch <= c->max_batch, SBD_E_INVALID, "sbd_tvprox: bad argument");
+    SBD_REQUIRE(maxiter >= 1, SBD_E_INVALID,
+                "sbd_tvprox: 'maxiter' is required (the reference leaves MaxIter undefined without it)");
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, batch);
+    set_chamb_options(c, lambda, maxiter, tol, tau);
+    zero_duals(c, batch);
+    chambolle(c, d_g, d_f, batch, maxiter);
+    fetch_chamb_state(c, batch, iters, err);
+    SBD_CATCH(c)
+}
+
+int sbd_tvprox(sbd_ctx* c, const double* g, double lambda, int maxiter, double tol, double tau,
+               const double* dual_px, const double* dual_py, double* f, double* px, double* py,
+               int* iters, double* err, int batch) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(g && f && batch >= 1 && batch <= c->max_batch, SBD_E_INVALID, "sbd_tvprox: bad argument");
+    SBD_REQUIRE(maxiter >= 1, SBD_E_INVALID,
+                "sbd_tvprox: 'maxiter' is required (the reference leaves MaxIter undefined without it)");
+    SBD_REQUIRE((dual_px == nullptr) == (dual_py == nullptr), SBD_E_INVALID, "sbd_tvprox: give both dual arrays or none");
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, batch);
+    const size_t bytes = sizeof(double) * batch * c->npix;
+    set_chamb_options(c, lambda, maxiter, tol, tau);
+    SBD_CUDA(cudaMemcpyAsync(c->X, g, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (dual_px) {
+        SBD_CUDA(cudaMemcpyAsync(c->px0, dual_px, bytes, cudaMemcpyHostToDevice, c->stream));
+        SBD_CUDA(cudaMemcpyAsync(c->py0, dual_py, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        zero_duals(c, batch);
+    }
+    chambolle(c, c->X, c->P, batch, maxiter);
+    SBD_CUDA(cudaMemcpyAsync(f, c->P, bytes, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<ChambState> h(batch);
+    SBD_CUDA(cudaMemcpyAsync(h.data(), c->chst, sizeof(ChambState) * batch, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < batch; ++b) {
+        if (iters) iters[b] = h[b].k;
+        if (err) err[b] = h[b].err;
+        const bool odd = h[b].k & 1;
+        if (px) SBD_CUDA(cudaMemcpyAsync(px + (size_t)b * c->npix, (odd ? c->px1 : c->px0) + (size_t)b * c->npix,
+                                         sizeof(double) * c->npix, cudaMemcpyDeviceToHost, c->stream));
+        if (py) SBD_CUDA(cudaMemcpyAsync(py + (size_t)b * c->npix, (odd ? c->py1 : c->py0) + (size_t)b * c->npix,
+                                         sizeof(double) * c->npix, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    SBD_CATCH(c)
+}
+
+// ---------------------------------------------------------------- likelihood closures
+static void set_params_device(sbd_ctx* c, double theta, double sigma2, const double psi[2], double prox_lambda,
+                              int maxiter, double tol, double tau) {
+    Control h;
+    memset(&h, 0, sizeof h);
+    h.theta = theta; h.sigma2 = sigma2; h.psi[0] = psi[0]; h.psi[1] = psi[1];
+    h.prox_lambda_theta = prox_lambda * theta;
+    h.inv_scale = 1.0 / (sigma2 * (double)c->npix);
+    h.tau = tau; h.tol = tol; h.maxiter = maxiter;
+    h.ii = 2; h.draw = 0; h.phase = 0; h.post_n = 0;
+    SBD_CUDA(cudaMemcpyAsync(c->ctl, &h, sizeof(Control), cudaMemcpyHostToDevice, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+int sbd_likelihood(sbd_ctx* c, const double* x, const double* y, const double psi[2], double sigma2,
+                   double theta, double scal[6], double* gradF) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(x && y && psi && scal, SBD_E_INVALID, "sbd_likelihood: bad argument");
+    require_pow2(c);
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, 1);
+    const size_t bytes = sizeof(double) * c->npix;
+    set_params_device(c, theta, sigma2, psi, 1.0, 1, 1e-3, 0.249);
+    SBD_CUDA(cudaMemcpyAsync(c->ximg, y, bytes, cudaMemcpyHostToDevice, c->stream));
+    rows_fwd(c, c->ximg, c->yhat, 1);
+    cols<COL_FWD>(c, c->yhat, c->yhat, 1);
+    SBD_CUDA(cudaMemcpyAsync(c->X, x, bytes, cudaMemcpyHostToDevice, c->stream));
+    psf_from_host(c, psi, c->nk);
+    tvnorm(c, c->X, c->stats, NSTAT, 1);
+    rows_fwd(c, c->X, c->S1, 1);
+    cols<COL_FWD_REDUCE>(c, c->S1, c->S1, 1);
+    if (gradF) {
+        cols<COL_MUL_INV>(c, c->S1, c->S2, 1);
+        rows_inv(c, c->S2, c->Gf, 1);
+        SBD_CUDA(cudaMemcpyAsync(gradF, c->Gf, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    double st[NSTAT];
+    SBD_CUDA(cudaMemcpyAsync(st, c->stats, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    const double dimX = (double)c->npix, tv = st[0], rss = st[1];
+    scal[0] = rss / (2.0 * sigma2);
+    scal[1] = st[2] / sigma2;
+    scal[2] = st[3] / sigma2;
+    scal[3] = rss / (2.0 * (sigma2 * sigma2)) - dimX / (2.0 * sigma2);
+    scal[4] = tv;
+    scal[5] = -scal[0] - theta * tv;
+    SBD_CATCH(c)
+}
+
+// ---------------------------------------------------------------- comm
+int sbd_comm_unique_id(char id[SBD_NCCL_ID_BYTES]) {
+    if (!id) return SBD_E_INVALID;
+    if (!g_nccl.load()) { g_create_error = "sbd_comm_unique_id: libnccl.so.2 not found"; return SBD_E_COMM; }
+    nccl_uid u;
+    if (g_nccl.GetUniqueId(&u) != 0) { g_create_error = "ncclGetUniqueId failed"; return SBD_E_COMM; }
+    memcpy(id, u.internal, SBD_NCCL_ID_BYTES);
+    return SBD_OK;
+}
+
+int sbd_comm_init(sbd_ctx* c, int nranks, int rank, const char id[SBD_NCCL_ID_BYTES]) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(id && nranks >= 1 && rank >= 0 && rank < nranks, SBD_E_INVALID, "sbd_comm_init: bad argument");
+    SBD_REQUIRE(g_nccl.load(), SBD_E_COMM, "sbd_comm_init: libnccl.so.2 not found");
+    SBD_CUDA(cudaSetDevice(c->device));
+    nccl_uid u;
+    memcpy(u.internal, id, SBD_NCCL_ID_BYTES);
+    nccl_comm comm = nullptr;
+    const int rc = g_nccl.CommInitRank(&comm, nranks, u, rank);
+    if (rc != 0)
+        throw Error{SBD_E_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")};
+    c->comm = comm; c->nranks = nranks; c->rank = rank;
+    SBD_CATCH(c)
+}
+
+int sbd_comm_destroy(sbd_ctx* c) {
+    if (!c) return SBD_E_INVALID;
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    c->comm = nullptr; c->nranks = 1; c->rank = 0;
+    return SBD_OK;
+}
+
+}  // extern "C"
+
+// ===========================================================================
+// SAPG driver
+// ===========================================================================
+namespace {
+
+struct DevTraces {
+    Traces t;
+    double* delta = nullptr;
+    std::vector<void*> owned;
+    ~DevTraces() { for (void* p : owned) cudaFree(p); }
+    template <typename T> T* mk(size_t n, cudaStream_t s) {
+        T* p = dalloc<T>(n);
+        owned.push_back(p);
+        SBD_CUDA(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), s));
+        return p;
+    }
+};
+
+// spectral analysis of the current X: tv, X^ (in S1) and the Parseval sums
+void analyse(sbd_ctx* c, int nch) {
+    { PhaseTimer pt(c, 4); tvnorm(c, c->X, c->stats, NSTAT, nch); }
+    { PhaseTimer pt(c, 5);
+      rows_fwd(c, c->X, c->S1, nch);
+      cols<COL_FWD_REDUCE>(c, c->S1, c->S1, nch); }
+}
+
+void gather_stats(sbd_ctx* c, int nch, const double** stats_out) {
+    if (c->comm) {
+        PhaseTimer pt(c, 7);
+        const int rc = g_nccl.AllGather(c->stats, c->allstats, (size_t)nch * NSTAT, NCCL_FLOAT64, c->comm, c->stream);
+        if (rc != 0) throw Error{SBD_E_COMM, "ncclAllGather failed"};
+        *stats_out = c->allstats;
+    } else {
+        *stats_out = c->stats;
+    }
+}
+
+void copy_trace(double* dst, const double* src, size_t n, cudaStream_t s) {
+    if (dst && n) SBD_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+}
+
+void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const double* d_xtrue,
+                   const sbd_params* prm, const double* d_noise, sbd_traces* out) {
+    require_pow2(c);
+    SBD_REQUIRE(prm && out, SBD_E_INVALID, "sbd_sapg_run: params/traces NULL");
+    const int nch = prm->n_chains;
+    SBD_REQUIRE(nch >= 1 && nch <= c->max_batch, SBD_E_INVALID, "sbd_sapg_run: n_chains must be in [1, max_batch]");
+    SBD_REQUIRE(prm->samples >= 1 && prm->warmup >= 0, SBD_E_INVALID, "sbd_sapg_run: samples >= 1, warmup >= 0");
+    SBD_REQUIRE(prm->chambolle_maxiter >= 1, SBD_E_INVALID, "sbd_sapg_run: chambolle_maxiter >= 1");
+    const int ntot = std::max(prm->total_chains, nch);
+    if (c->comm) SBD_REQUIRE(ntot == nch * c->nranks, SBD_E_INVALID, "sbd_sapg_run: total_chains must be n_chains * nranks");
+    else SBD_REQUIRE(ntot == nch, SBD_E_COMM, "sbd_sapg_run: total_chains > n_chains needs sbd_comm_init");
+    ensure_ws(c, nch);
+    cudaStream_t s = c->stream;
+    for (int i = 0; i < SBD_N_PHASES; ++i) { c->phase_ms[i] = 0.0; c->phase_calls[i] = 0; }
+    const bool want_profile = c->profile;
+    c->profile = false;             // phases are timed over the main loop only
+
+    const int samples = prm->samples, warmup = prm->warmup, burnIn = prm->burnIn;
+    const int npsi = (c->model == SBD_LAPLACE) ? 1 : 2;
+    SapgConst k;
+    memset(&k, 0, sizeof k);
+    k.model = c->model; k.t = c->t; k.npsi = npsi; k.phi = c->phi;
+    k.gam = prm->gam; k.lamb = prm->lamb; k.sq2gam = std::sqrt(2.0 * prm->gam); k.prox_lambda = prm->prox_lambda;
+    k.min_th = prm->min_th; k.max_th = prm->max_th; k.c_theta = prm->c_theta;
+    for (int p = 0; p < 2; ++p) {
+        k.psi_min[p] = prm->psi_min[p]; k.psi_max[p] = prm->psi_max[p]; k.c_psi[p] = prm->c_psi[p];
+        k.psi_fixed[p] = prm->psi_fixed[p]; k.fix_psi[p] = prm->fix_psi[p];
+    }
+    k.sigma2_min = std::min(prm->sigma2_min, prm->sigma2_max);      // Guassian.m:51-52
+    k.sigma2_max = std::max(prm->sigma2_min, prm->sigma2_max);
+    k.c_sigma2 = prm->c_sigma2; k.sigma2_fixed = prm->sigma2_fixed; k.fix_sigma = prm->fix_sigma;
+    k.dimX = (double)c->npix; k.n_local = nch; k.n_total = ntot;
+    k.burnIn = burnIn; k.samples = samples; k.warmup = warmup; k.has_xtrue = d_xtrue != nullptr;
+
+    // device traces
+    DevTraces dt;
+    dt.t.logPiWU = dt.mk<double>(std::max(warmup, 1), s);
+    dt.t.thetas = dt.mk<double>(samples, s); dt.t.sigmas = dt.mk<double>(samples, s);
+    dt.t.psi0 = dt.mk<double>(samples, s); dt.t.psi1 = dt.mk<double>(samples, s);
+    dt.t.g_theta = dt.mk<double>(samples, s); dt.t.g_psi0 = dt.mk<double>(samples, s);
+    dt.t.g_psi1 = dt.mk<double>(samples, s); dt.t.g_sigma = dt.mk<double>(samples, s);
+    dt.t.logPi = dt.mk<double>(samples, s); dt.t.gX = dt.mk<double>(samples, s);
+    dt.t.sqerr = dt.mk<double>(samples, s); dt.t.chamb_k = dt.mk<int>(samples, s);
+    {
+        std::vector<double> hd(samples + 1, 0.0);
+        for (int i = 1; i <= samples; ++i)                          // delta(i), Guassian.m:55
+            hd[i] = prm->d_scale * (std::pow((double)i, -prm->d_exp) / k.dimX);
+        dt.delta = dt.mk<double>(samples + 1, s);
+        SBD_CUDA(cudaMemcpyAsync(dt.delta, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice, s));
+        SBD_CUDA(cudaStreamSynchronize(s));
+        dt.t.delta = dt.delta;
+    }
+    dfree(c->allstats);
+    c->allstats = dalloc<double>((size_t)ntot * NSTAT);
+    double* post = nullptr;
+    if (prm->post_mean) {
+        if (c->post_batch < nch) { dfree(c->post); c->post = dalloc<double>((size_t)nch * c->npix); c->post_batch = nch; }
+        post = c->post;
+        SBD_CUDA(cudaMemsetAsync(post, 0, sizeof(double) * nch * c->npix, s));
+    }
+
+    cudaEvent_t ev0, ev1;
+    SBD_CUDA(cudaEventCreate(&ev0)); SBD_CUDA(cudaEventCreate(&ev1));
+    SBD_CUDA(cudaEventRecord(ev0, s));
+
+    // ---- setup: parameters(1), Y^, X = X0 on every chain
+    double psi0v[2] = {prm->psi_init[0], prm->psi_init[1]};
+    set_params_device(c, prm->th_init, prm->sigma2_init, psi0v, prm->prox_lambda, prm->chambolle_maxiter,
+                      prm->chambolle_tol, prm->chambolle_tau);
+    k_psf_taps<<<1, 256, 0, s>>>(c->model, c->t, c->phi, c->ctl, nullptr, c->taps);
+    LAUNCH_CHECK(c);
+    psf_refresh_coef(c, c->nk);
+    SBD_CUDA(cudaMemcpyAsync(c->ximg, d_y, sizeof(double) * c->npix, cudaMemcpyDeviceToDevice, s));
+    rows_fwd(c, c->ximg, c->yhat, 1);
+    cols<COL_FWD>(c, c->yhat, c->yhat, 1);
+    k_bcast_image<<<(unsigned)((c->npix + 255) / 256), 256, 0, s>>>(d_X0 ? d_X0 : d_y, c->X, c->npix, nch);
+    LAUNCH_CHECK(c);
+    if (d_xtrue) {
+        k_sqdiff<<<dim3(256, nch), 256, 0, s>>>(c->X, d_xtrue, c->npix, c->part_sq, c->cnt_sq, c->stats);
+        LAUNCH_CHECK(c);
+        double st[NSTAT];
+        SBD_CUDA(cudaMemcpyAsync(st, c->stats, sizeof st, cudaMemcpyDeviceToHost, s));
+        SBD_CUDA(cudaStreamSynchronize(s));
+        out->err_warm0 = 10.0 * std::log10(st[4] / k.dimX);        // laplace.m:28 via utils/MSE.m:3
+    }
+
+    const double* gstats = nullptr;
+    auto prox = [&]() {
+        PhaseTimer pt(c, 3);
+        zero_duals(c, nch);                                        // chambolle_prox_TV_stop.m:68-69
+        chambolle(c, c->X, c->P, nch, prm->chambolle_maxiter);
+    };
+    auto myula_step = [&]() {
+        { PhaseTimer pt(c, 0);
+          cols<COL_MUL_INV>(c, c->S1, c->S2, nch);                 // gradF with the current parameters
+          rows_inv(c, c->S2, c->Gf, nch); }
+        { PhaseTimer pt(c, 1);
+          const unsigned gx = (unsigned)((c->npix / 2 + 255) / 256);
+          k_langevin<<<dim3(gx, nch), 256, 0, s>>>(c->X, c->P, c->Gf, d_noise, post, c->ctl, k.gam, k.lamb, k.sq2gam,
+                                                   c->npix, nch, prm->seed, prm->chain_offset, burnIn);
+          LAUNCH_CHECK(c); }
+        prox();
+        analyse(c, nch);
+        if (d_xtrue) {
+            k_sqdiff<<<dim3(256, nch), 256, 0, s>>>(c->X, d_xtrue, c->npix, c->part_sq, c->cnt_sq, c->stats);
+            LAUNCH_CHECK(c);
+        }
+        gather_stats(c, nch, &gstats);
+    };
+    auto scalar = [&](int mode) {
+        PhaseTimer pt(c, 6);
+        k_sapg_scalar<<<1, 256, 0, s>>>(mode, k, c->ctl, gstats, c->chst, dt.t, c->taps);
+        LAUNCH_CHECK(c);
+        if (mode == 2) psf_refresh_coef(c, c->nk);
+    };
+
+    // ---- warm-up (Guassian.m:67-93)
+    analyse(c, nch);
+    prox();                                                         // :76
+    for (int ii = 2; ii <= warmup; ++ii) {                          // :78
+        myula_step();
+        scalar(1);
+    }
+    if (out->X_warm)
+        SBD_CUDA(cudaMemcpyAsync(out->X_warm, c->X, sizeof(double) * nch * c->npix, cudaMemcpyDeviceToHost, s));
+
+    // ---- main loop (Guassian.m:137-248).  The state after warm-up already holds
+    // prox(X, theta(1)) (:140) and the statistics of X for logPiTraceX(1) (:137).
+    gather_stats(c, nch, &gstats);      // (also lines the ranks up before the timed main loop)
+    scalar(0);
+    c->profile = want_profile;
+    cudaEvent_t evm;
+    SBD_CUDA(cudaEventCreate(&evm));
+    SBD_CUDA(cudaEventRecord(evm, s));
+    const long long launches0 = c->launches;
+    for (int ii = 2; ii <= samples; ++ii) {                         // :158
+        myula_step();
+        scalar(2);
+    }
+    SBD_CUDA(cudaEventRecord(ev1, s));
+    out->launches_main = c->launches - launches0;
+    c->profile = false;
+
+    // ---- err_psf on the device, then bring the trajectories home
+    double* d_errpsf = dt.mk<double>(samples, s);
+    k_err_psf<<<samples, 256, 0, s>>>(c->model, c->t, c->phi, dt.t.psi0, dt.t.psi1, prm->err_psf_lag,
+                                      prm->psi_true[0], prm->psi_true[1], samples, d_errpsf);
+    LAUNCH_CHECK(c);
+
+    std::vector<double> th(samples), sg(samples), p0(samples), p1(samples), sq(samples);
+    SBD_CUDA(cudaMemcpyAsync(th.data(), dt.t.thetas, sizeof(double) * samples, cudaMemcpyDeviceToHost, s));
+    SBD_CUDA(cudaMemcpyAsync(sg.data(), dt.t.sigmas, sizeof(double) * samples, cudaMemcpyDeviceToHost, s));
+    SBD_CUDA(cudaMemcpyAsync(p0.data(), dt.t.psi0, sizeof(double) * samples, cudaMemcpyDeviceToHost, s));
+    SBD_CUDA(cudaMemcpyAsync(p1.data(), dt.t.psi1, sizeof(double) * samples, cudaMemcpyDeviceToHost, s));
+    SBD_CUDA(cudaMemcpyAsync(sq.data(), dt.t.sqerr, sizeof(double) * samples, cudaMemcpyDeviceToHost, s));
+    copy_trace(out->logPiTrace_WU, dt.t.logPiWU, warmup, s);
+    copy_trace(out->grad_theta, dt.t.g_theta, samples, s);
+    copy_trace(out->grad_psi0, dt.t.g_psi0, samples, s);
+    copy_trace(out->grad_psi1, dt.t.g_psi1, samples, s);
+    copy_trace(out->grad_sigma, dt.t.g_sigma, samples, s);
+    copy_trace(out->logPiTraceX, dt.t.logPi, samples, s);
+    copy_trace(out->gXTrace, dt.t.gX, samples, s);
+    copy_trace(out->err_psf, d_errpsf, samples, s);
+    if (out->chambolle_iters)
+        SBD_CUDA(cudaMemcpyAsync(out->chambolle_iters, dt.t.chamb_k, sizeof(int) * samples, cudaMemcpyDeviceToHost, s));
+    if (out->X_last)
+        SBD_CUDA(cudaMemcpyAsync(out->X_last, c->X, sizeof(double) * nch * c->npix, cudaMemcpyDeviceToHost, s));
+    if (out->X_mean && post) {
+        k_chain_mean<<<(unsigned)((c->npix + 255) / 256), 256, 0, s>>>(post, c->Gf, c->npix, nch);
+        LAUNCH_CHECK(c);
+        SBD_CUDA(cudaMemcpyAsync(out->X_mean, c->Gf, sizeof(double) * c->npix, cudaMemcpyDeviceToHost, s));
+    }
+    SBD_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    SBD_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    out->seconds = ms * 1e-3;
+    SBD_CUDA(cudaEventElapsedTime(&ms, evm, ev1));
+    out->seconds_main = ms * 1e-3;
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evm);
+    c->profile = want_profile;
+    resolve_phase_events(c);
+    out->last_samp = samples;                                       // Guassian.m:252 (no early break, Q10)
+
+    // ---- host post-processing of the scalar trajectories (Guassian.m:218-247,258-284)
+    if (out->thetas) memcpy(out->thetas, th.data(), sizeof(double) * samples);
+    if (out->sigmas) memcpy(out->sigmas, sg.data(), sizeof(double) * samples);
+    if (out->psi0) memcpy(out->psi0, p0.data(), sizeof(double) * samples);
+    if (out->psi1) memcpy(out->psi1, p1.data(), sizeof(double) * samples);
+    if (out->err_sample)
+        for (int i = 0; i < samples; ++i)
+            out->err_sample[i] = d_xtrue ? 10.0 * std::log10(sq[i] / k.dimX) : 0.0;    // utils/MSE.m:3
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    const std::vector<double>* trj[4] = {&th, &p0, &p1, &sg};
+    double* tolv[4] = {out->tol_theta, out->tol_psi0, out->tol_psi1, out->tol_sigma};
+    double* meanv[4] = {out->mean_theta, out->mean_psi0, out->mean_psi1, out->mean_sigma};
+    for (int q = 0; q < 4; ++q) {
+        const std::vector<double>& v = *trj[q];
+        double run = 0.0;           // sum(v(burnIn:ii))
+        double prev_mean = nan;     // mean(v(burnIn:ii-1)); empty range -> NaN (Q11)
+        if (tolv[q]) tolv[q][0] = 0.0;
+        for (int ii = 1; ii <= samples; ++ii) {
+            double mean = nan;
+            if (burnIn >= 1 && ii >= burnIn) {
+                run += v[ii - 1];
+                mean = run / (double)(ii - burnIn + 1);
+            }
+            if (ii >= 2 && tolv[q]) tolv[q][ii - 1] = std::fabs(mean - prev_mean) / prev_mean;   // :218-231
+            if (ii > burnIn && ii >= 2 && meanv[q] && burnIn >= 1) meanv[q][ii - burnIn - 1] = mean;  // :236-244
+            prev_mean = mean;
+        }
+        out->EB[q] = (burnIn >= 1 && samples >= burnIn) ? run / (double)(samples - burnIn + 1) : nan;   // :258 (Q12)
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sbd_sapg_run_dev(sbd_ctx* c, const double* d_y, const double* d_X0, const sbd_params* prm, sbd_traces* out) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(d_y, SBD_E_INVALID, "sbd_sapg_run_dev: y is NULL");
+    SBD_CUDA(cudaSetDevice(c->device));
+    sapg_run_impl(c, d_y, d_X0, nullptr, prm, nullptr, out);
+    SBD_CATCH(c)
+}
+
+int sbd_sapg_run(sbd_ctx* c, const double* y, const double* X0, const double* x_true,
+                 const sbd_params* prm, const double* noise, sbd_traces* out) {
+    if (!c) return SBD_E_INVALID;
+    double *d_y = nullptr, *d_x0 = nullptr, *d_xt = nullptr, *d_nz = nullptr;
+    int rc = SBD_OK;
+    try {
+        SBD_REQUIRE(y && prm && out, SBD_E_INVALID, "sbd_sapg_run: y/params/traces NULL");
+        SBD_CUDA(cudaSetDevice(c->device));
+        const size_t bytes = sizeof(double) * c->npix;
+        d_y = dalloc<double>(c->npix);
+        SBD_CUDA(cudaMemcpyAsync(d_y, y, bytes, cudaMemcpyHostToDevice, c->stream));
+        if (X0) { d_x0 = dalloc<double>(c->npix); SBD_CUDA(cudaMemcpyAsync(d_x0, X0, bytes, cudaMemcpyHostToDevice, c->stream)); }
+        if (x_true) { d_xt = dalloc<double>(c->npix); SBD_CUDA(cudaMemcpyAsync(d_xt, x_true, bytes, cudaMemcpyHostToDevice, c->stream)); }
+        if (noise) {
+            const size_t draws = (size_t)std::max(prm->warmup - 1, 0) + (size_t)std::max(prm->samples - 1, 0);
+            const size_t n = draws * (size_t)prm->n_chains * c->npix;
+            d_nz = dalloc<double>(n);
+            SBD_CUDA(cudaMemcpyAsync(d_nz, noise, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        }
+        sapg_run_impl(c, d_y, d_x0, d_xt, prm, d_nz, out);
+    } catch (const Error& e) {
+        rc = fail(c, e);
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_y); cudaFree(d_x0); cudaFree(d_xt); cudaFree(d_nz);
+    return rc;
+}
+
+}  // extern "C"
