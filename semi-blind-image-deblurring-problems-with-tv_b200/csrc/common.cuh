@@ -48,7 +48,9 @@ struct ChambState {             // one per image / chain
     int done;                   // stop flag (k >= maxiter || err <= tol)
     double err;                 // err of the last executed sweep
     unsigned int counter;       // last-block-done ticket
-    unsigned int pad;
+    int redo;                   // fused kernel: number of levels the redo launch must apply (0 = none)
+    int buf;                    // which buffer of the ping-pong pair holds the current dual pair
+    int pad;
 };
 
 struct SapgConst {              // constants of a run (device copy)

@@ -7,6 +7,7 @@
 #include "philox.cuh"
 #include "psf.cuh"
 #include "tv.cuh"
+#include "tv_multi.cuh"
 #include "fft.cuh"
 #include "sapg.cuh"
 
@@ -71,6 +72,7 @@ struct sbd_ctx {
 
     // geometry
     int tvV = 1, tv_gx = 1, tv_gy = 1, tv_seg = 8, tv_parts = 1;
+    int cmT = 5, cm_strips = 1, cm_gx = 1, cm_gy = 1, cm_seg = 128;     // fused Chambolle geometry
     int rowsLP = 1, rowsT = 32, colsC = 2, colsT = 32, ntiles = 1;
     int geom_batch = -1;
 
@@ -159,6 +161,20 @@ void set_geometry(sbd_ctx* c, int batch) {
     c->tv_seg = seg;
     c->tv_gy = (ny + seg - 1) / seg;
     c->tv_parts = c->tv_gx * c->tv_gy;
+    {   // fused multi-sweep Chambolle kernel (tv_multi.cuh): T levels, strips of 64 - 2*HL output pixels
+        int T = 4;
+        if (const char* e = getenv("SBD_CHAMB_T")) T = atoi(e);
+        if (nx % 2 != 0 || nx < 8) T = 1;           // pairs of pixels must be 16-byte aligned
+        c->cmT = (T == 3 || T == 4 || T == 5) ? T : 1;
+        const int HL = (c->cmT + 1) & ~1, WO = 64 - 2 * HL;
+        c->cm_strips = (nx + WO - 1) / WO;
+        c->cm_gx = (c->cm_strips + TV_WARPS - 1) / TV_WARPS;
+        int sg = 128;
+        while (sg > 16 && (long long)c->cm_gx * ((ny + sg - 1) / sg) * batch < 6 * 148) sg /= 2;
+        if (const char* e = getenv("SBD_CHAMB_SEG")) sg = std::max(1, atoi(e));
+        c->cm_seg = sg;
+        c->cm_gy = (ny + sg - 1) / sg;
+    }
     if (c->pow2) {
         int LP = std::max(1, 4096 / nx);
         LP = std::min(LP, ny / 2);
@@ -201,7 +217,7 @@ void ensure_ws(sbd_ctx* c, int batch) {
     const int strips = (c->nx + 31) / 32;
     const size_t maxparts = (size_t)((strips + TV_WARPS - 1) / TV_WARPS) * c->ny;    // seg = 1 bound
     c->part_tv = dalloc<double>((size_t)batch * maxparts);
-    c->part_ch = dalloc<double>((size_t)batch * maxparts);
+    c->part_ch = dalloc<double>((size_t)batch * maxparts * 5);     // up to T = 5 levels per launch
     c->part_col = dalloc<double>((size_t)batch * (c->nk + 1) * 4);
     c->part_sq = dalloc<double>((size_t)batch * 1024);
     c->ws_batch = batch;
@@ -250,21 +266,47 @@ void tvnorm(sbd_ctx* c, const double* x, double* out, int out_stride, int batch)
 // prox with the options stored in ctl (prox_lambda_theta, tau, tol, maxiter).
 // `maxiter` is the host copy used to size the launch sequence.  The dual pair
 // starts from px0/py0 (caller zeroes or fills them).
+template <int T>
+void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const double* pyi, double* pxo,
+                        double* pyo, int batch, int redo) {
+    dim3 grid(c->cm_gx, c->cm_gy, batch);
+    k_chamb_multi<T><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg, c->cm_strips,
+                                                          c->npix, c->ctl, c->chst, c->part_ch, redo);
+}
+
 void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter) {
     k_chamb_reset<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->chst, batch);
     LAUNCH_CHECK(c);
     dim3 grid(c->tv_gx, c->tv_gy, batch);
     PhaseTimer* pt = new PhaseTimer(c, 2);
-    for (int s = 0; s < maxiter; ++s) {
-        const double* pxi = (s & 1) ? c->px1 : c->px0;
-        const double* pyi = (s & 1) ? c->py1 : c->py0;
-        double* pxo = (s & 1) ? c->px0 : c->px1;
-        double* pyo = (s & 1) ? c->py0 : c->py1;
-        if (c->tvV == 2)
-            k_chamb_sweep<2><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst, c->part_ch);
-        else
-            k_chamb_sweep<1><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst, c->part_ch);
-        LAUNCH_CHECK(c);
+    if (c->cmT > 1) {
+        // blocks of T fused sweeps; each block = main launch + redo launch (no-op unless the
+        // reference's stop test fired inside the block)
+        const int T = c->cmT, nblk = (maxiter + T - 1) / T;
+        for (int b = 0; b < nblk; ++b) {
+            const double* pxi = (b & 1) ? c->px1 : c->px0;
+            const double* pyi = (b & 1) ? c->py1 : c->py0;
+            double* pxo = (b & 1) ? c->px0 : c->px1;
+            double* pyo = (b & 1) ? c->py0 : c->py1;
+            for (int redo = 0; redo < 2; ++redo) {
+                if (T == 3) chamb_multi_launch<3>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                else if (T == 4) chamb_multi_launch<4>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                else chamb_multi_launch<5>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                LAUNCH_CHECK(c);
+            }
+        }
+    } else {
+        for (int s = 0; s < maxiter; ++s) {
+            const double* pxi = (s & 1) ? c->px1 : c->px0;
+            const double* pyi = (s & 1) ? c->py1 : c->py0;
+            double* pxo = (s & 1) ? c->px0 : c->px1;
+            double* pyo = (s & 1) ? c->py0 : c->py1;
+            if (c->tvV == 2)
+                k_chamb_sweep<2><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst, c->part_ch);
+            else
+                k_chamb_sweep<1><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst, c->part_ch);
+            LAUNCH_CHECK(c);
+        }
     }
     delete pt;
     if (c->tvV == 2)
@@ -623,7 +665,7 @@ int sbd_tvprox(sbd_ctx* c, const double* g, double lambda, int maxiter, double t
     for (int b = 0; b < batch; ++b) {
         if (iters) iters[b] = h[b].k;
         if (err) err[b] = h[b].err;
-        const bool odd = h[b].k & 1;
+        const bool odd = h[b].buf != 0;
         if (px) SBD_CUDA(cudaMemcpyAsync(px + (size_t)b * c->npix, (odd ? c->px1 : c->px0) + (size_t)b * c->npix,
                                          sizeof(double) * c->npix, cudaMemcpyDeviceToHost, c->stream));
         if (py) SBD_CUDA(cudaMemcpyAsync(py + (size_t)b * c->npix, (odd ? c->py1 : c->py0) + (size_t)b * c->npix,

@@ -245,6 +245,7 @@ k_chamb_sweep(const double* __restrict__ g, const double* __restrict__ pxi,
                 const double err = sqrt(tot);                               // :128  (...)^0.5
                 const int k = st[img].k + 1;                                // :121
                 st[img].k = k;
+                st[img].buf ^= 1;
                 st[img].err = err;
                 st[img].done = !((k < ctl->maxiter) && (err > ctl->tol));   // :131
             }
@@ -253,7 +254,7 @@ k_chamb_sweep(const double* __restrict__ g, const double* __restrict__ pxi,
 }
 
 // f = g - lambda * DivergenceIm(px, py)                  chambolle_prox_TV_stop.m:149
-// The dual pair lives in buffer (k & 1) of the ping-pong pair.
+// The dual pair lives in buffer st.buf of the ping-pong pair.
 template <int V>
 __global__ void __launch_bounds__(TV_THREADS)
 k_chamb_out(const double* __restrict__ g, const double* __restrict__ px0,
@@ -264,7 +265,7 @@ k_chamb_out(const double* __restrict__ g, const double* __restrict__ px0,
     const StripGeom s = strip_geom<V>(nx, ny, seg);
     if (!s.warp_on) return;
     const double lambda = ctl->prox_lambda_theta;
-    const bool odd = (st[img].k & 1) != 0;
+    const bool odd = st[img].buf != 0;
     const size_t off = (size_t)img * img_stride;
     const double* px = (odd ? px1 : px0) + off;
     const double* py = (odd ? py1 : py0) + off;
@@ -298,7 +299,7 @@ k_chamb_out(const double* __restrict__ g, const double* __restrict__ px0,
 
 __global__ void k_chamb_reset(ChambState* st, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { st[i].k = 0; st[i].done = 0; st[i].err = 0.0; st[i].counter = 0u; }
+    if (i < n) { st[i].k = 0; st[i].done = 0; st[i].err = 0.0; st[i].counter = 0u; st[i].redo = 0; st[i].buf = 0; }
 }
 
 }  // namespace sbd
