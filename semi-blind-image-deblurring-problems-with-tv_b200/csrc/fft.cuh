@@ -8,24 +8,53 @@
 // and the reductions of op.f / op.grad_w1 / op.grad_w2 / op.gradF_sigma
 // (run_Gaussian_demo.m:171-175) through Parseval (DESIGN.md "Fusion identities").
 //
+// 1-D engine: mixed-radix Stockham (radices 16/8/4), at most three stages per
+// size; every thread owns 16 complex values per stage.  The first stage reads
+// its operands straight from global memory and the last stage writes its results
+// straight to global memory, so a 4096-point transform makes only two trips
+// through shared memory (one per stage boundary).  Twiddles come from a table
+// in global memory (L1-resident): fp64 issue slots are the scarce resource here.
+//
 // 2-D real FFT of an nx x ny image (nx = fast axis):
 //   rows pass  : two real lines per complex length-nx FFT (z = a + i b), split
-//                into the two half spectra -> spec[q][k], k = 0..nx/2
+//                into the two half spectra
 //   column pass: C adjacent bins k per block, length-ny complex FFT along q.
+// Half-spectrum layout ("tile-major"): spec[tile][q][c], tile = k / C, c = k % C,
+// so that the column pass streams one contiguous ny*C*16-byte chunk per block;
+// the strided side of the transpose lands on the rows pass, whose 32..128-byte
+// pieces of neighbouring lines are combined by the L2.
 #pragma once
 #include "common.cuh"
 #include "psf.cuh"
 
 namespace sbd {
 
-constexpr int FFT_ITER = 4;                 // radix-4 butterflies held in registers per thread
+// ---------------------------------------------------------------------------
+// plans: radices per size (product = N), first radix = shared-memory pad period
+// ---------------------------------------------------------------------------
+template <int N> struct FftPlan;
+template <> struct FftPlan<4096> { static constexpr int NST = 3, R0 = 16, R1 = 16, R2 = 16; };
+template <> struct FftPlan<2048> { static constexpr int NST = 3, R0 = 16, R1 = 16, R2 = 8; };
+template <> struct FftPlan<1024> { static constexpr int NST = 3, R0 = 16, R1 = 16, R2 = 4; };
+template <> struct FftPlan<512>  { static constexpr int NST = 3, R0 = 8,  R1 = 8,  R2 = 8; };
+template <> struct FftPlan<256>  { static constexpr int NST = 2, R0 = 16, R1 = 16, R2 = 1; };
+template <> struct FftPlan<128>  { static constexpr int NST = 2, R0 = 16, R1 = 8,  R2 = 1; };
+template <> struct FftPlan<64>   { static constexpr int NST = 2, R0 = 8,  R1 = 8,  R2 = 1; };
+template <> struct FftPlan<32>   { static constexpr int NST = 2, R0 = 8,  R1 = 4,  R2 = 1; };
+template <> struct FftPlan<16>   { static constexpr int NST = 2, R0 = 4,  R1 = 4,  R2 = 1; };
 
-template <int N> struct ILog2 { static constexpr int v = 1 + ILog2<N / 2>::v; };
-template <> struct ILog2<1> { static constexpr int v = 0; };
+// padded position inside a line: one spare element every R0 positions keeps the
+// stride-R0 writes of the first stage off the same shared-memory banks
+template <int N>
+__device__ __forceinline__ int fft_pad(int p) { return p + p / FftPlan<N>::R0; }
+template <int N>
+constexpr int fft_line_elems() { return N + N / FftPlan<N>::R0; }
 
-// (x,y) * (-i) forward, * (+i) inverse
+// ---------------------------------------------------------------------------
+// small DFTs in registers (natural order in, natural order out)
+// ---------------------------------------------------------------------------
 template <bool INV>
-__device__ __forceinline__ double2 mul_mi(double2 a) {
+__device__ __forceinline__ double2 mul_mi(double2 a) {          // a * (-i) forward, a * (+i) inverse
     return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
 }
 template <bool INV>
@@ -34,162 +63,235 @@ __device__ __forceinline__ double2 twid(const double2* __restrict__ tw, int idx)
     if (INV) w.y = -w.y;
     return w;
 }
-
-// One radix-4 Stockham stage over B lines of length N stored at s[b*ld + n].
-// Every thread of the block must call this (contains __syncthreads()).
-template <int N, int NS, bool INV>
-__device__ __forceinline__ void stockham_r4(double2* __restrict__ s, int ld, int B,
-                                            const double2* __restrict__ tw) {
-    constexpr int Q = N / 4;
-    const int total = B * Q;
-    double2 r[FFT_ITER][4];
-    int dst[FFT_ITER];
-#pragma unroll
-    for (int it = 0; it < FFT_ITER; ++it) {
-        const int idx = threadIdx.x + it * blockDim.x;
-        dst[it] = -1;
-        if (idx < total) {
-            const int b = idx / Q, j = idx - b * Q;
-            const int k = j & (NS - 1);
-            const double2* L = s + b * ld;
-            double2 a0 = L[j], a1 = L[j + Q], a2 = L[j + 2 * Q], a3 = L[j + 3 * Q];
-            if (NS > 1) {
-                constexpr int STEP = N / (4 * NS);
-                a1 = cmul(a1, twid<INV>(tw, k * STEP));
-                a2 = cmul(a2, twid<INV>(tw, 2 * k * STEP));
-                a3 = cmul(a3, twid<INV>(tw, 3 * k * STEP));
-            }
-            const double2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
-            const double2 t2 = cadd(a1, a3), t3 = mul_mi<INV>(csub(a1, a3));
-            r[it][0] = cadd(t0, t2);
-            r[it][1] = cadd(t1, t3);
-            r[it][2] = csub(t0, t2);
-            r[it][3] = csub(t1, t3);
-            dst[it] = b * ld + ((j - k) << 2) + k;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < FFT_ITER; ++it) {
-        if (dst[it] >= 0) {
-            double2* D = s + dst[it];
-            D[0] = r[it][0]; D[NS] = r[it][1]; D[2 * NS] = r[it][2]; D[3 * NS] = r[it][3];
-        }
-    }
-    __syncthreads();
+template <bool INV>
+__device__ __forceinline__ void dft4(double2& a0, double2& a1, double2& a2, double2& a3) {
+    const double2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    const double2 t2 = cadd(a1, a3), t3 = mul_mi<INV>(csub(a1, a3));
+    a0 = cadd(t0, t2); a1 = cadd(t1, t3); a2 = csub(t0, t2); a3 = csub(t1, t3);
+}
+// multiply by W_16^m (forward) or its conjugate (inverse), m = 0..9
+template <bool INV, int M>
+__device__ __forceinline__ double2 mul_w16(double2 a) {
+    if (M == 0) return a;
+    if (M == 4) return mul_mi<INV>(a);
+    if (M == 8) return make_double2(-a.x, -a.y);
+    constexpr double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173, H = 0.70710678118654752440;
+    constexpr double c = (M == 1) ? C1 : (M == 2) ? H : (M == 3) ? S1 : (M == 6) ? -H : (M == 9) ? -C1 : 0.0;
+    constexpr double s = (M == 1) ? S1 : (M == 2) ? H : (M == 3) ? C1 : (M == 6) ? H : (M == 9) ? -S1 : 0.0;
+    // forward twiddle = c - i s
+    const double si = INV ? -s : s;
+    return make_double2(fma(a.x, c, a.y * si), fma(a.y, c, -a.x * si));
 }
 
-// Final radix-2 stage (NS = N/2) when log2(N) is odd.
-template <int N, bool INV>
-__device__ __forceinline__ void stockham_r2_last(double2* __restrict__ s, int ld, int B,
-                                                 const double2* __restrict__ tw) {
-    constexpr int H = N / 2;
-    const int total = B * H;
-    double2 r[2 * FFT_ITER][2];
-    int dst[2 * FFT_ITER];
+template <int R, bool INV> struct Dft;
+template <bool INV> struct Dft<4, INV> {
+    static __device__ __forceinline__ void run(double2* v) { dft4<INV>(v[0], v[1], v[2], v[3]); }
+};
+template <bool INV> struct Dft<8, INV> {
+    // n = 2 n1 + n2 (R1 = 4 over n1, R2 = 2 over n2), k = k1 + 4 k2
+    static __device__ __forceinline__ void run(double2* v) {
+        double2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+        double2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+        dft4<INV>(e0, e1, e2, e3);
+        dft4<INV>(o0, o1, o2, o3);
+        o1 = mul_w16<INV, 2>(o1); o2 = mul_w16<INV, 4>(o2); o3 = mul_w16<INV, 6>(o3);
+        v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+        v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+        v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+        v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+    }
+};
+template <bool INV> struct Dft<16, INV> {
+    // n = 4 n1 + n2, k = k1 + 4 k2: DFT4 over n1, twiddle W16^(n2 k1), DFT4 over n2
+    static __device__ __forceinline__ void run(double2* v) {
+        double2 y[4][4];
 #pragma unroll
-    for (int it = 0; it < 2 * FFT_ITER; ++it) {
-        const int idx = threadIdx.x + it * blockDim.x;
-        dst[it] = -1;
-        if (idx < total) {
-            const int b = idx / H, j = idx - b * H;
-            const double2* L = s + b * ld;
-            const double2 a0 = L[j];
-            const double2 a1 = cmul(L[j + H], twid<INV>(tw, j));
-            r[it][0] = cadd(a0, a1);
-            r[it][1] = csub(a0, a1);
-            dst[it] = b * ld + j;
+        for (int n2 = 0; n2 < 4; ++n2) {
+            y[n2][0] = v[n2]; y[n2][1] = v[4 + n2]; y[n2][2] = v[8 + n2]; y[n2][3] = v[12 + n2];
+            dft4<INV>(y[n2][0], y[n2][1], y[n2][2], y[n2][3]);
+        }
+        y[1][1] = mul_w16<INV, 1>(y[1][1]); y[1][2] = mul_w16<INV, 2>(y[1][2]); y[1][3] = mul_w16<INV, 3>(y[1][3]);
+        y[2][1] = mul_w16<INV, 2>(y[2][1]); y[2][2] = mul_w16<INV, 4>(y[2][2]); y[2][3] = mul_w16<INV, 6>(y[2][3]);
+        y[3][1] = mul_w16<INV, 3>(y[3][1]); y[3][2] = mul_w16<INV, 6>(y[3][2]); y[3][3] = mul_w16<INV, 9>(y[3][3]);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            dft4<INV>(y[0][k1], y[1][k1], y[2][k1], y[3][k1]);
+            v[k1] = y[0][k1]; v[k1 + 4] = y[1][k1]; v[k1 + 8] = y[2][k1]; v[k1 + 12] = y[3][k1];
         }
     }
-    __syncthreads();
+};
+
+// ---------------------------------------------------------------------------
+// one Stockham stage for the 16 values a thread owns.
+//   tl  : thread index inside the line, 0 .. N/16-1
+//   src(p) -> double2 : operand at (unpadded) position p of the line
+//   dst(p, v)         : result for position p
+// The 16/R butterflies of a thread are jb = tl + m*N/16.
+// ---------------------------------------------------------------------------
+template <int N, int R, int NS, bool INV, class Src>
+__device__ __forceinline__ void stage_load(int tl, double2 (&v)[16], Src src, const double2* __restrict__ tw) {
+    constexpr int M = 16 / R, TL = N / 16, Q = N / R;
 #pragma unroll
-    for (int it = 0; it < 2 * FFT_ITER; ++it) {
-        if (dst[it] >= 0) { s[dst[it]] = r[it][0]; s[dst[it] + H] = r[it][1]; }
+    for (int m = 0; m < M; ++m) {
+        const int jb = tl + m * TL;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[m * R + r] = src(jb + r * Q);
+        if (NS > 1) {
+            const int k = jb & (NS - 1);
+            constexpr int STEP = N / (NS * R);
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[m * R + r] = cmul(v[m * R + r], twid<INV>(tw, r * k * STEP));
+        }
+        Dft<R, INV>::run(&v[m * R]);
+    }
+}
+template <int N, int R, int NS, class Dst>
+__device__ __forceinline__ void stage_store(int tl, const double2 (&v)[16], Dst dst) {
+    constexpr int M = 16 / R, TL = N / 16;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int jb = tl + m * TL;
+        const int k = jb & (NS - 1);
+        const int base = (jb - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) dst(base + r * NS, v[m * R + r]);
+    }
+}
+
+// Full transform of the line(s) a block holds.  src0 feeds the first stage, dstL
+// receives the last stage; the stage boundaries go through the shared-memory
+// line `s` (padded, element stride `cs`, i.e. position p lives at s[fft_pad(p)*cs]).
+// `active` threads own data; every thread of the block must call this.
+template <int N, bool INV, bool SYNC_LAST, class Src, class Dst>
+__device__ __forceinline__ void fft_run(bool active, int tl, double2* __restrict__ s, int cs,
+                                        const double2* __restrict__ tw, Src src0, Dst dstL) {
+    // SYNC_LAST: the last stage writes into the same shared-memory line it reads (in place)
+    using P = FftPlan<N>;
+    double2 v[16];
+    auto smem_src = [&](int p) { return s[fft_pad<N>(p) * cs]; };
+    auto smem_dst = [&](int p, double2 x) { s[fft_pad<N>(p) * cs] = x; };
+    if (active) {
+        stage_load<N, P::R0, 1, INV>(tl, v, src0, tw);
+        stage_store<N, P::R0, 1>(tl, v, smem_dst);
     }
     __syncthreads();
-}
-
-template <int N, int NS, bool INV>
-__device__ __forceinline__ void stockham_stages(double2* s, int ld, int B, const double2* tw) {
-    if constexpr (NS * 4 <= N) {
-        stockham_r4<N, NS, INV>(s, ld, B, tw);
-        stockham_stages<N, NS * 4, INV>(s, ld, B, tw);
-    } else if constexpr (NS * 2 == N) {
-        stockham_r2_last<N, INV>(s, ld, B, tw);
+    if constexpr (P::NST == 3) {
+        if (active) stage_load<N, P::R1, P::R0, INV>(tl, v, smem_src, tw);
+        __syncthreads();
+        if (active) stage_store<N, P::R1, P::R0>(tl, v, smem_dst);
+        __syncthreads();
+        if (active) stage_load<N, P::R2, P::R0 * P::R1, INV>(tl, v, smem_src, tw);
+        if (SYNC_LAST) __syncthreads();
+        if (active) stage_store<N, P::R2, P::R0 * P::R1>(tl, v, dstL);
+    } else {
+        if (active) stage_load<N, P::R1, P::R0, INV>(tl, v, smem_src, tw);
+        if (SYNC_LAST) __syncthreads();
+        if (active) stage_store<N, P::R1, P::R0>(tl, v, dstL);
     }
-}
-
-// In-place FFT of B lines (natural order in, natural order out).  The caller
-// must __syncthreads() after filling `s`; on return the data is synchronised.
-// Threads required: B*N/(4*FFT_ITER) (at least 32).
-template <int N, bool INV>
-__device__ __forceinline__ void fft_lines(double2* s, int ld, int B, const double2* tw) {
-    stockham_stages<N, 1, INV>(s, ld, B, tw);
 }
 
 // ---------------------------------------------------------------------------
-// rows pass, forward: real lines -> half spectra
-// grid = (ny/2/LP, batch), dynamic smem = LP*N*16 bytes
+// half-spectrum addressing (tile-major)
+// ---------------------------------------------------------------------------
+struct SpecGeom {
+    int C, logC, ny;            // bins per tile, log2(C), number of lines
+};
+__device__ __forceinline__ size_t spec_idx(const SpecGeom& g, int k, int q) {
+    return ((size_t)(k >> g.logC) * g.ny + q) * g.C + (k & (g.C - 1));
+}
+
+// ---------------------------------------------------------------------------
+// rows pass, forward: real lines -> half spectra.  One block = LP line pairs.
+// grid = (ny/2/LP, batch), block = max(32, LP*N/16), smem = LP*fft_line_elems<N>()*16
 // ---------------------------------------------------------------------------
 template <int N>
-__global__ void k_rows_fwd(const double* __restrict__ x, double2* __restrict__ spec, int sp, int LP,
+__global__ void k_rows_fwd(const double* __restrict__ x, double2* __restrict__ spec, SpecGeom sg, int LP,
                            size_t img_stride, size_t spec_stride, const double2* __restrict__ tw) {
     extern __shared__ double2 fsm[];
+    constexpr int TL = N / 16, LE = fft_line_elems<N>();
     const int img = blockIdx.y;
     const int line0 = 2 * blockIdx.x * LP;
-    const double* xi = x + (size_t)img * img_stride + (size_t)line0 * N;
-    double2* so = spec + (size_t)img * spec_stride + (size_t)line0 * sp;
-    for (int e = threadIdx.x; e < LP * N; e += blockDim.x) {
-        const int b = e / N, n = e - b * N;
-        const double* p = xi + (size_t)(2 * b) * N + n;
-        fsm[e] = make_double2(__ldg(p), __ldg(p + N));
-    }
+    const bool active = threadIdx.x < LP * TL;
+    const int b = threadIdx.x / TL, tl = threadIdx.x - b * TL;
+    const double* xa = x + (size_t)img * img_stride + (size_t)(line0 + 2 * b) * N;
+    double2* line = fsm + (size_t)b * LE;
+    // every stage lands in shared memory: the split below needs Z[k] and Z[N-k] together
+    auto src = [&](int p) { return make_double2(__ldg(xa + p), __ldg(xa + N + p)); };
+    auto dst = [&](int p, double2 v) { line[fft_pad<N>(p)] = v; };
+    fft_run<N, false, true>(active, tl, line, 1, tw, src, dst);
     __syncthreads();
-    fft_lines<N, false>(fsm, N, LP, tw);
+    double2* so = spec + (size_t)img * spec_stride;
     constexpr int HB = N / 2 + 1;
     for (int e = threadIdx.x; e < LP * HB; e += blockDim.x) {
-        const int b = e / HB, k = e - b * HB;
-        const double2 zk = fsm[b * N + k], zm = fsm[b * N + ((N - k) & (N - 1))];
-        so[(size_t)(2 * b) * sp + k] = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
-        so[(size_t)(2 * b + 1) * sp + k] = make_double2(0.5 * (zk.y + zm.y), 0.5 * (zm.x - zk.x));
+        const int bb = e / HB, k = e - bb * HB;
+        const double2* L = fsm + (size_t)bb * LE;
+        const double2 zk = L[fft_pad<N>(k)], zm = L[fft_pad<N>((N - k) & (N - 1))];
+        const int ja = line0 + 2 * bb;
+        so[spec_idx(sg, k, ja)] = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+        so[spec_idx(sg, k, ja + 1)] = make_double2(0.5 * (zk.y + zm.y), 0.5 * (zm.x - zk.x));
     }
 }
 
 // rows pass, inverse: half spectra -> real lines (unnormalised; the 1/(nx*ny)
 // factor is folded into the spectral multiply of the column pass)
 template <int N>
-__global__ void k_rows_inv(const double2* __restrict__ spec, double* __restrict__ out, int sp, int LP,
+__global__ void k_rows_inv(const double2* __restrict__ spec, double* __restrict__ out, SpecGeom sg, int LP,
                            size_t img_stride, size_t spec_stride, const double2* __restrict__ tw) {
     extern __shared__ double2 fsm[];
+    constexpr int TL = N / 16, LE = fft_line_elems<N>();
     const int img = blockIdx.y;
     const int line0 = 2 * blockIdx.x * LP;
-    const double2* si = spec + (size_t)img * spec_stride + (size_t)line0 * sp;
-    double* xo = out + (size_t)img * img_stride + (size_t)line0 * N;
+    const double2* si = spec + (size_t)img * spec_stride;
     constexpr int HB = N / 2 + 1;
     for (int e = threadIdx.x; e < LP * HB; e += blockDim.x) {
-        const int b = e / HB, k = e - b * HB;
-        const double2 A = __ldg(si + (size_t)(2 * b) * sp + k);
-        const double2 Bv = __ldg(si + (size_t)(2 * b + 1) * sp + k);
+        const int bb = e / HB, k = e - bb * HB;
+        double2* L = fsm + (size_t)bb * LE;
+        const int ja = line0 + 2 * bb;
+        const double2 A = __ldg(si + spec_idx(sg, k, ja));
+        const double2 Bv = __ldg(si + spec_idx(sg, k, ja + 1));
         if (k == 0 || k == N / 2) {
-            fsm[b * N + k] = make_double2(A.x, Bv.x);       // C2R: imaginary parts of the real bins dropped
+            L[fft_pad<N>(k)] = make_double2(A.x, Bv.x);     // C2R: imaginary parts of the real bins dropped
         } else {
-            fsm[b * N + k] = make_double2(A.x - Bv.y, A.y + Bv.x);
-            fsm[b * N + N - k] = make_double2(A.x + Bv.y, Bv.x - A.y);
+            L[fft_pad<N>(k)] = make_double2(A.x - Bv.y, A.y + Bv.x);
+            L[fft_pad<N>(N - k)] = make_double2(A.x + Bv.y, Bv.x - A.y);
         }
     }
     __syncthreads();
-    fft_lines<N, true>(fsm, N, LP, tw);
-    for (int e = threadIdx.x; e < LP * N; e += blockDim.x) {
-        const int b = e / N, n = e - b * N;
-        const double2 z = fsm[e];
-        double* p = xo + (size_t)(2 * b) * N + n;
-        p[0] = z.x;
-        p[N] = z.y;
+    const bool active = threadIdx.x < LP * TL;
+    const int b = threadIdx.x / TL, tl = threadIdx.x - b * TL;
+    double2* line = fsm + (size_t)b * LE;
+    double* xo = out + (size_t)img * img_stride + (size_t)(line0 + 2 * b) * N;
+    // the first stage reads the packed spectrum from shared memory; it must finish
+    // reading before the in-place writes of the same stage start
+    using P = FftPlan<N>;
+    double2 v[16];
+    auto smem_src = [&](int p) { return line[fft_pad<N>(p)]; };
+    auto smem_dst = [&](int p, double2 z) { line[fft_pad<N>(p)] = z; };
+    auto gdst = [&](int p, double2 z) { xo[p] = z.x; xo[N + p] = z.y; };
+    if (active) stage_load<N, P::R0, 1, true>(tl, v, smem_src, tw);
+    __syncthreads();
+    if (active) stage_store<N, P::R0, 1>(tl, v, smem_dst);
+    __syncthreads();
+    if constexpr (P::NST == 3) {
+        if (active) stage_load<N, P::R1, P::R0, true>(tl, v, smem_src, tw);
+        __syncthreads();
+        if (active) stage_store<N, P::R1, P::R0>(tl, v, smem_dst);
+        __syncthreads();
+        if (active) {
+            stage_load<N, P::R2, P::R0 * P::R1, true>(tl, v, smem_src, tw);
+            stage_store<N, P::R2, P::R0 * P::R1>(tl, v, gdst);
+        }
+    } else {
+        if (active) {
+            stage_load<N, P::R1, P::R0, true>(tl, v, smem_src, tw);
+            stage_store<N, P::R1, P::R0>(tl, v, gdst);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
-// column pass.  grid = (ceil(nk/C), batch); dynamic smem = C*N*16 bytes.
+// column pass.  grid = (ntiles, batch); block = max(32, C*N/16);
+// dynamic smem = C*fft_line_elems<N>()*16 bytes.  Thread -> (tl, c), c fastest.
 // ---------------------------------------------------------------------------
 enum ColMode {
     COL_FWD = 0,            // spectrum of y (no PSF work)
@@ -209,7 +311,7 @@ struct ColArgs {
     unsigned int* counters; // [batch]
     double* stats;          // [batch][NSTAT] (rss -> 1, c0 -> 2, c1 -> 3), already divided by nx*ny
     size_t spec_stride;
-    int sp, nk, nxfull, t, npsi, C, opsel;
+    int nk, nxfull, t, npsi, C, logC, opsel;
     double opscale;
 };
 
@@ -218,11 +320,14 @@ __global__ void k_cols(const ColArgs a) {
     extern __shared__ double2 fsm[];
     __shared__ double2 coefS[8][3][MAXT];
     __shared__ double redS[3 * 32];
+    constexpr int TL = N / 16;
     const int img = blockIdx.y;
     const int C = a.C;
     const int k0 = blockIdx.x * C;
-    const double2* in = a.in + (size_t)img * a.spec_stride;
-    double2* out = a.out + (size_t)img * a.spec_stride;
+    const size_t tile_off = (size_t)img * a.spec_stride + (size_t)blockIdx.x * N * C;
+    const double2* in = a.in + tile_off;
+    double2* out = a.out + tile_off;
+    const double2* yh = a.yhat + (size_t)blockIdx.x * N * C;
 
     if (MODE != COL_FWD) {
         for (int e = threadIdx.x; e < C * 3 * a.t; e += blockDim.x) {
@@ -230,75 +335,108 @@ __global__ void k_cols(const ColArgs a) {
             const int k = min(k0 + c, a.nk - 1);
             coefS[c][m][j] = __ldg(a.coef + ((size_t)m * a.nk + k) * MAXT + j);
         }
-        __syncthreads();
-    }
-
-    // ---- load (+ spectral multiply for MUL_INV)
-    for (int e = threadIdx.x; e < C * N; e += blockDim.x) {
-        const int c = e % C, q = e / C;
-        const int k = k0 + c;
-        double2 v = make_double2(0.0, 0.0);
-        if (k < a.nk) {
-            v = __ldg(in + (size_t)q * a.sp + k);
-            if (MODE == COL_MUL_INV) {
-                const double2 w = __ldg(a.tw + q);
-                const double2 H = psf_horner(coefS[c][0], a.t, w);
-                const double2 yv = __ldg(a.yhat + (size_t)q * a.sp + k);
-                const double2 R = csub(cmul(H, v), yv);                 // H X^ - Y^
-                const double2 G = cmulc(R, H);                          // conj(H) R
-                const double sc = a.ctl->inv_scale;
-                v = make_double2(G.x * sc, G.y * sc);
-            }
-        }
-        fsm[c * N + q] = v;
     }
     __syncthreads();
 
-    if (MODE == COL_MUL_INV) {
-        fft_lines<N, true>(fsm, N, C, a.tw);
-    } else {
-        fft_lines<N, false>(fsm, N, C, a.tw);
-    }
+    const bool active = threadIdx.x < C * TL;
+    const int c = threadIdx.x & (C - 1), tl = threadIdx.x >> a.logC;
+    const int k = k0 + c;
+    const bool kin = k < a.nk;                       // the last tile may be partly empty
+    double2* line = fsm + c;                         // element stride C between positions
+    double acc[3] = {0.0, 0.0, 0.0};
+
+    auto gsrc = [&](int q) {
+        double2 v = __ldg(in + (size_t)q * C + c);
+        if (MODE == COL_MUL_INV) {
+            const double2 w = __ldg(a.tw + q);
+            const double2 H = psf_horner(coefS[c][0], a.t, w);
+            const double2 yv = __ldg(yh + (size_t)q * C + c);
+            const double2 R = csub(cmul(H, v), yv);                 // H X^ - Y^
+            const double2 G = cmulc(R, H);                          // conj(H) R
+            const double sc = a.ctl->inv_scale;
+            v = make_double2(G.x * sc, G.y * sc);
+        }
+        return v;
+    };
+    auto gdst = [&](int q, double2 v) {
+        if (!kin) return;
+        out[(size_t)q * C + c] = v;
+        if (MODE == COL_FWD_REDUCE) {
+            const double2 w = __ldg(a.tw + q);
+            const double2 yv = __ldg(yh + (size_t)q * C + c);
+            const double2 H = psf_horner(coefS[c][0], a.t, w);
+            const double2 R = csub(cmul(H, v), yv);
+            // Hermitian weights of the half spectrum: interior bins count twice
+            const double wt = (k == 0 || 2 * k == a.nxfull) ? 1.0 : 2.0;
+            acc[0] += wt * (R.x * R.x + R.y * R.y);
+            const double2 T0 = cmul(psf_horner(coefS[c][1], a.t, w), v);
+            acc[1] += wt * (T0.x * R.x + T0.y * R.y);               // Re conj(D0 X^) R
+            if (a.npsi > 1) {
+                const double2 T1 = cmul(psf_horner(coefS[c][2], a.t, w), v);
+                acc[2] += wt * (T1.x * R.x + T1.y * R.y);
+            }
+        }
+    };
 
     if (MODE == COL_OP) {
-        for (int e = threadIdx.x; e < C * N; e += blockDim.x) {
-            const int c = e % C, q = e / C;
+        // forward transform ending in shared memory, multiply, inverse transform from shared memory
+        auto sdst = [&](int q, double2 v) {
             const double2 w = __ldg(a.tw + q);
             const int m = (a.opsel == SBD_OP_A || a.opsel == SBD_OP_AT) ? 0 : (a.opsel == SBD_OP_D0 ? 1 : 2);
             double2 K = psf_horner(coefS[c][m], a.t, w);
             if (a.opsel == SBD_OP_AT) K.y = -K.y;
-            const double2 v = cmul(K, fsm[c * N + q]);
-            fsm[c * N + q] = make_double2(v.x * a.opscale, v.y * a.opscale);
+            const double2 z = cmul(K, v);
+            line[fft_pad<N>(q) * C] = make_double2(z.x * a.opscale, z.y * a.opscale);
+        };
+        auto ssrc = [&](int q) { return line[fft_pad<N>(q) * C]; };
+        using P = FftPlan<N>;
+        // the last forward stage writes in place: all its reads are done (stage_load precedes
+        // stage_store inside fft_run only for the fused case), so run it split by hand
+        double2 v[16];
+        auto smem_src = [&](int p) { return line[fft_pad<N>(p) * C]; };
+        auto smem_dst = [&](int p, double2 x) { line[fft_pad<N>(p) * C] = x; };
+        if (active) { stage_load<N, P::R0, 1, false>(tl, v, gsrc, a.tw); stage_store<N, P::R0, 1>(tl, v, smem_dst); }
+        __syncthreads();
+        if constexpr (P::NST == 3) {
+            if (active) stage_load<N, P::R1, P::R0, false>(tl, v, smem_src, a.tw);
+            __syncthreads();
+            if (active) stage_store<N, P::R1, P::R0>(tl, v, smem_dst);
+            __syncthreads();
+            if (active) stage_load<N, P::R2, P::R0 * P::R1, false>(tl, v, smem_src, a.tw);
+            __syncthreads();
+            if (active) stage_store<N, P::R2, P::R0 * P::R1>(tl, v, sdst);
+        } else {
+            if (active) stage_load<N, P::R1, P::R0, false>(tl, v, smem_src, a.tw);
+            __syncthreads();
+            if (active) stage_store<N, P::R1, P::R0>(tl, v, sdst);
         }
         __syncthreads();
-        fft_lines<N, true>(fsm, N, C, a.tw);
-    }
-
-    // ---- store (+ reductions for FWD_REDUCE)
-    double acc[3] = {0.0, 0.0, 0.0};
-    for (int e = threadIdx.x; e < C * N; e += blockDim.x) {
-        const int c = e % C, q = e / C;
-        const int k = k0 + c;
-        if (k < a.nk) {
-            const double2 v = fsm[c * N + q];
-            out[(size_t)q * a.sp + k] = v;
-            if (MODE == COL_FWD_REDUCE) {
-                const double2 w = __ldg(a.tw + q);
-                const double2 yv = __ldg(a.yhat + (size_t)q * a.sp + k);
-                const double2 H = psf_horner(coefS[c][0], a.t, w);
-                const double2 R = csub(cmul(H, v), yv);
-                // Hermitian weights of the half spectrum: interior bins count twice
-                const double wt = (k == 0 || 2 * k == a.nxfull) ? 1.0 : 2.0;
-                acc[0] += wt * (R.x * R.x + R.y * R.y);
-                const double2 T0 = cmul(psf_horner(coefS[c][1], a.t, w), v);
-                acc[1] += wt * (T0.x * R.x + T0.y * R.y);               // Re conj(D0 X^) R
-                if (a.npsi > 1) {
-                    const double2 T1 = cmul(psf_horner(coefS[c][2], a.t, w), v);
-                    acc[2] += wt * (T1.x * R.x + T1.y * R.y);
-                }
+        // inverse: first stage reads shared memory and writes it in place
+        if (active) stage_load<N, P::R0, 1, true>(tl, v, ssrc, a.tw);
+        __syncthreads();
+        if (active) stage_store<N, P::R0, 1>(tl, v, smem_dst);
+        __syncthreads();
+        if constexpr (P::NST == 3) {
+            if (active) stage_load<N, P::R1, P::R0, true>(tl, v, smem_src, a.tw);
+            __syncthreads();
+            if (active) stage_store<N, P::R1, P::R0>(tl, v, smem_dst);
+            __syncthreads();
+            if (active) {
+                stage_load<N, P::R2, P::R0 * P::R1, true>(tl, v, smem_src, a.tw);
+                stage_store<N, P::R2, P::R0 * P::R1>(tl, v, gdst);
+            }
+        } else {
+            if (active) {
+                stage_load<N, P::R1, P::R0, true>(tl, v, smem_src, a.tw);
+                stage_store<N, P::R1, P::R0>(tl, v, gdst);
             }
         }
+    } else if (MODE == COL_MUL_INV) {
+        fft_run<N, true, false>(active, tl, line, C, a.tw, gsrc, gdst);
+    } else {
+        fft_run<N, false, false>(active, tl, line, C, a.tw, gsrc, gdst);
     }
+
     if (MODE == COL_FWD_REDUCE) {
         block_sum<3>(acc, redS);
         const unsigned int ntiles = gridDim.x;

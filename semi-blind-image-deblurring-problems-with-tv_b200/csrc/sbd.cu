@@ -73,7 +73,10 @@ struct sbd_ctx {
     // geometry
     int tvV = 1, tv_gx = 1, tv_gy = 1, tv_seg = 8, tv_parts = 1;
     int cmT = 5, cm_strips = 1, cm_gx = 1, cm_gy = 1, cm_seg = 128;     // fused Chambolle geometry
-    int rowsLP = 1, rowsT = 32, colsC = 2, colsT = 32, ntiles = 1;
+    bool cm_pipe = false;
+    int cm_minb = 3;
+    int rowsLP = 1, rowsT = 32, colsC = 2, colsLogC = 1, colsT = 32, ntiles = 1;
+    size_t rows_smem = 0, cols_smem = 0;
     int geom_batch = -1;
 
     // device buffers
@@ -165,6 +168,7 @@ void set_geometry(sbd_ctx* c, int batch) {
         int T = 4;
         if (const char* e = getenv("SBD_CHAMB_T")) T = atoi(e);
         if (nx % 2 != 0 || nx < 8) T = 1;           // pairs of pixels must be 16-byte aligned
+        if (const char* e = getenv("SBD_CHAMB_MINB")) c->cm_minb = atoi(e);
         c->cmT = (T == 3 || T == 4 || T == 5) ? T : 1;
         const int HL = (c->cmT + 1) & ~1, WO = 64 - 2 * HL;
         c->cm_strips = (nx + WO - 1) / WO;
@@ -176,19 +180,15 @@ void set_geometry(sbd_ctx* c, int batch) {
         c->cm_gy = (ny + sg - 1) / sg;
     }
     if (c->pow2) {
-        int LP = std::max(1, 4096 / nx);
-        LP = std::min(LP, ny / 2);
+        // rows pass: LP line pairs per block, shared memory <= ~74 KB so that 3 blocks fit an SM
+        const size_t le_x = (size_t)nx + nx / (nx >= 1024 || nx == 256 || nx == 128 ? 16 : (nx == 16 ? 4 : 8));
+        int LP = 1;
+        while (2 * LP <= ny / 2 && (size_t)(2 * LP) * le_x * 16 <= 74 * 1024 && 2 * LP * nx <= 4096) LP *= 2;
         while (LP > 1 && (long long)(ny / 2 / LP) * batch < 2 * 148) LP /= 2;
         c->rowsLP = LP;
-        c->rowsT = std::max(32, LP * nx / (4 * FFT_ITER));
-        int C = 8;
-        const size_t cap = (ny >= 2048) ? 128 * 1024 : 64 * 1024;
-        while (C > 2 && (size_t)C * ny * 16 > cap) C /= 2;
-        if (const char* e = getenv("SBD_COLS_C")) C = std::max(1, std::min(8, atoi(e)));
-        while (C > 1 && ((size_t)C * ny / (4 * FFT_ITER) > 1024 || (size_t)C * ny * 16 > 200 * 1024)) C /= 2;
-        c->colsC = C;
-        c->colsT = std::max(32, C * ny / (4 * FFT_ITER));
-        c->ntiles = (c->nk + C - 1) / C;
+        c->rowsT = std::max(32, LP * nx / 16);
+        c->rows_smem = (size_t)LP * le_x * 16;
+        c->colsT = std::max(32, c->colsC * ny / 16);
     }
     c->geom_batch = batch;
 }
@@ -266,12 +266,12 @@ void tvnorm(sbd_ctx* c, const double* x, double* out, int out_stride, int batch)
 // prox with the options stored in ctl (prox_lambda_theta, tau, tol, maxiter).
 // `maxiter` is the host copy used to size the launch sequence.  The dual pair
 // starts from px0/py0 (caller zeroes or fills them).
-template <int T>
+template <int T, int MINB>
 void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const double* pyi, double* pxo,
                         double* pyo, int batch, int redo) {
     dim3 grid(c->cm_gx, c->cm_gy, batch);
-    k_chamb_multi<T><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg, c->cm_strips,
-                                                          c->npix, c->ctl, c->chst, c->part_ch, redo);
+    k_chamb_multi<T, false, MINB><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
+                                                                       c->cm_strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
 }
 
 void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter) {
@@ -289,9 +289,18 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter) {
             double* pxo = (b & 1) ? c->px0 : c->px1;
             double* pyo = (b & 1) ? c->py0 : c->py1;
             for (int redo = 0; redo < 2; ++redo) {
-                if (T == 3) chamb_multi_launch<3>(c, g, pxi, pyi, pxo, pyo, batch, redo);
-                else if (T == 4) chamb_multi_launch<4>(c, g, pxi, pyi, pxo, pyo, batch, redo);
-                else chamb_multi_launch<5>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                const int mb = c->cm_minb;
+                if (T == 3) {
+                    if (mb == 5) chamb_multi_launch<3, 5>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                    else if (mb == 4) chamb_multi_launch<3, 4>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                    else chamb_multi_launch<3, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                } else if (T == 4) {
+                    if (mb == 4) chamb_multi_launch<4, 4>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                    else chamb_multi_launch<4, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                } else {
+                    if (mb == 3) chamb_multi_launch<5, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                    else chamb_multi_launch<5, 2>(c, g, pxi, pyi, pxo, pyo, batch, redo);
+                }
                 LAUNCH_CHECK(c);
             }
         }
@@ -329,12 +338,19 @@ void set_smem(K kernel, size_t bytes) {
 
 #define SBD_FFT_SIZES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
 
+SpecGeom spec_geom(const sbd_ctx* c) {
+    SpecGeom g;
+    g.C = c->colsC; g.logC = c->colsLogC; g.ny = c->ny;
+    return g;
+}
+
 void rows_fwd(sbd_ctx* c, const double* x, double2* spec, int batch) {
-    const size_t smem = (size_t)c->rowsLP * c->nx * sizeof(double2);
+    const size_t smem = c->rows_smem;
     dim3 g(c->ny / 2 / c->rowsLP, batch);
+    const SpecGeom sg = spec_geom(c);
     switch (c->nx) {
 #define X(N) case N: set_smem(k_rows_fwd<N>, smem); \
-        k_rows_fwd<N><<<g, c->rowsT, smem, c->stream>>>(x, spec, c->sp, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
+        k_rows_fwd<N><<<g, c->rowsT, smem, c->stream>>>(x, spec, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
         SBD_FFT_SIZES(X)
 #undef X
         default: throw Error{SBD_E_UNSUPPORTED, "rows_fwd: unsupported size"};
@@ -343,11 +359,12 @@ void rows_fwd(sbd_ctx* c, const double* x, double2* spec, int batch) {
 }
 
 void rows_inv(sbd_ctx* c, const double2* spec, double* out, int batch) {
-    const size_t smem = (size_t)c->rowsLP * c->nx * sizeof(double2);
+    const size_t smem = c->rows_smem;
     dim3 g(c->ny / 2 / c->rowsLP, batch);
+    const SpecGeom sg = spec_geom(c);
     switch (c->nx) {
 #define X(N) case N: set_smem(k_rows_inv<N>, smem); \
-        k_rows_inv<N><<<g, c->rowsT, smem, c->stream>>>(spec, out, c->sp, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
+        k_rows_inv<N><<<g, c->rowsT, smem, c->stream>>>(spec, out, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
         SBD_FFT_SIZES(X)
 #undef X
         default: throw Error{SBD_E_UNSUPPORTED, "rows_inv: unsupported size"};
@@ -360,10 +377,10 @@ void cols(sbd_ctx* c, const double2* in, double2* out, int batch, int opsel = 0)
     ColArgs a;
     a.in = in; a.out = out; a.yhat = c->yhat; a.coef = c->coef; a.tw = c->tw_ny; a.ctl = c->ctl;
     a.partials = c->part_col; a.counters = c->cnt_col; a.stats = c->stats;
-    a.spec_stride = c->spec_elems; a.sp = c->sp; a.nk = c->nk; a.nxfull = c->nx; a.t = c->t;
-    a.npsi = (c->model == SBD_LAPLACE) ? 1 : 2; a.C = c->colsC; a.opsel = opsel;
+    a.spec_stride = c->spec_elems; a.nk = c->nk; a.nxfull = c->nx; a.t = c->t;
+    a.npsi = (c->model == SBD_LAPLACE) ? 1 : 2; a.C = c->colsC; a.logC = c->colsLogC; a.opsel = opsel;
     a.opscale = 1.0 / ((double)c->nx * (double)c->ny);
-    const size_t smem = (size_t)c->colsC * c->ny * sizeof(double2);
+    const size_t smem = c->cols_smem;
     dim3 g(c->ntiles, batch);
     switch (c->ny) {
 #define X(N) case N: set_smem(k_cols<N, MODE>, smem); \
@@ -462,8 +479,24 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
         c->npix = (size_t)rows * cols;
         c->pow2 = is_pow2(rows) && is_pow2(cols) && rows >= 16 && cols >= 16 && rows <= 4096 && cols <= 4096;
         c->nk = rows / 2 + 1;
-        c->sp = (c->nk + 7) / 8 * 8;
-        c->spec_elems = (size_t)c->sp * cols;
+        c->sp = 0;
+        if (c->pow2) {
+            // column pass: C bins per block (tile-major half spectrum); padded line of ny elements
+            const size_t le_y = (size_t)cols + cols / (cols >= 1024 || cols == 256 || cols == 128 ? 16 : (cols == 16 ? 4 : 8));
+            int C = 8;
+            const size_t cap = (cols >= 2048) ? 144 * 1024 : 74 * 1024;
+            while (C > 1 && (size_t)C * le_y * 16 > cap) C /= 2;
+            if (const char* e = getenv("SBD_COLS_C")) {
+                const int v = atoi(e);
+                if (v == 1 || v == 2 || v == 4 || v == 8) C = v;
+            }
+            while (C > 1 && ((size_t)C * cols / 16 > 1024 || (size_t)C * le_y * 16 > 220 * 1024)) C /= 2;
+            c->colsC = C;
+            c->colsLogC = (C == 8) ? 3 : (C == 4) ? 2 : (C == 2) ? 1 : 0;
+            c->ntiles = (c->nk + C - 1) / C;
+            c->cols_smem = (size_t)C * le_y * 16;
+        }
+        c->spec_elems = (size_t)c->ntiles * cols * c->colsC;
         c->profile = getenv("SBD_PROFILE") && atoi(getenv("SBD_PROFILE")) != 0;
         SBD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->taps = dalloc<double>(3 * MAXT * MAXT);

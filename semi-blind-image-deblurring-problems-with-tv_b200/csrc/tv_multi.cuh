@@ -29,24 +29,25 @@ __device__ __forceinline__ double fast_rcp_seed(double a) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     return y;
 }
-// sqrt(a) for a >= 0 (a == 0 -> exactly 0): MUFU seed + two Goldschmidt steps (~1 ulp)
-__device__ __forceinline__ double fast_sqrt(double a) {
+// tmp = sqrt(a) (a >= 0; a == 0 -> exactly 0) and rinv = 1/(1 + tau*tmp), ~1 ulp each.
+// MUFU seeds + Goldschmidt / Newton steps; the reciprocal seed is taken from the
+// first (2^-20) sqrt estimate so that its MUFU latency overlaps the refinement.
+__device__ __forceinline__ void fast_sqrt_rcp(double a, double tau, double& tmp, double& rinv) {
     const double y = fast_rsqrt_seed(a + 1e-300);
     double g = a * y, h = 0.5 * y;
+    double rs = fast_rcp_seed(fma(tau, g, 1.0));
     double r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
     r = fma(-g, h, 0.5);
     g = fma(g, r, g);
-    return g;
-}
-// 1/d for d >= 1: MUFU seed + two Newton steps (~1 ulp)
-__device__ __forceinline__ double fast_rcp(double d) {
-    double r = fast_rcp_seed(d);
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double d = fma(tau, g, 1.0);
+    double e = fma(-d, rs, 1.0);
+    rs = fma(rs, e, rs);
+    e = fma(-d, rs, 1.0);
+    rs = fma(rs, e, rs);
+    e = fma(-d, rs, 1.0);           // third step: the seed saw d only to ~2^-20
+    rs = fma(rs, e, rs);
+    tmp = g; rinv = rs;
 }
 
 struct CmPk { double px[2], py[2], g[2]; };             // a row travelling up the levels
@@ -92,8 +93,8 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
     for (int v = 0; v < 2; ++v) {
         const double upy = un[v] - h.u[v];
         const double s2 = fma(upx[v], upx[v], upy * upy);
-        const double tmp = fast_sqrt(s2);                                    // :127
-        const double rinv = fast_rcp(fma(tau, tmp, 1.0));
+        double tmp, rinv;
+        fast_sqrt_rcp(s2, tau, tmp, rinv);                                   // :127 and 1/(1 + tau*tmp)
         const double ex = fma(tmp, h.px[v], -upx[v]), ey = fma(tmp, h.py[v], -upy);
         e += fma(ex, ex, ey * ey);                                           // :128
         o.px[v] = fma(tau, upx[v], h.px[v]) * rinv;                          // :129
@@ -113,17 +114,18 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
 
 template <bool EDGE>
 __device__ __forceinline__ void cm_load(CmPk& p, const double* __restrict__ g, const double* __restrict__ px,
-                                        const double* __restrict__ py, size_t off, const CmLane& L, double invlam) {
+                                        const double* __restrict__ py, size_t off, const CmLane& L) {
+    // raw values only: nothing here may depend on the loaded data, or the prefetch would stall
     if (!EDGE) {
         const double2 a = __ldg(reinterpret_cast<const double2*>(px + off));
         const double2 b = __ldg(reinterpret_cast<const double2*>(py + off));
         const double2 c = __ldg(reinterpret_cast<const double2*>(g + off));
         p.px[0] = a.x; p.px[1] = a.y; p.py[0] = b.x; p.py[1] = b.y;
-        p.g[0] = c.x * invlam; p.g[1] = c.y * invlam;
+        p.g[0] = c.x; p.g[1] = c.y;
     } else {
         p.px[0] = L.in0 ? __ldg(px + off) : 0.0;      p.px[1] = L.in1 ? __ldg(px + off + 1) : 0.0;
         p.py[0] = L.in0 ? __ldg(py + off) : 0.0;      p.py[1] = L.in1 ? __ldg(py + off + 1) : 0.0;
-        p.g[0] = L.in0 ? __ldg(g + off) * invlam : 0.0; p.g[1] = L.in1 ? __ldg(g + off + 1) * invlam : 0.0;
+        p.g[0] = L.in0 ? __ldg(g + off) : 0.0;        p.g[1] = L.in1 ? __ldg(g + off + 1) : 0.0;
     }
 }
 
@@ -140,87 +142,116 @@ __device__ __forceinline__ void cm_store(const CmPk& p, double* __restrict__ pxo
     }
 }
 
-// One generic step of the march (row r arrives): honours the row flags.
-template <int T, bool EDGE>
-__device__ __forceinline__ void cm_generic_iter(int r, CmLv (&h)[T], CmPk& nxt, double (&err)[T],
+// Schedule.  PIPE = false: in iteration r level s receives row r - s, which level
+// s-1 emitted earlier in the same iteration (levels run bottom-up, one dependent
+// chain).  PIPE = true: the levels are software-pipelined - level s consumes the
+// row level s-1 emitted in the PREVIOUS iteration (row r - 2s), the levels run
+// top-down and the T level steps of one iteration are independent (more ILP,
+// more registers).  inbox[s] is the row waiting for level s.
+__device__ __forceinline__ void cm_take(CmPk& dst, const CmPk& raw, double invlam) {
+    dst.px[0] = raw.px[0]; dst.px[1] = raw.px[1]; dst.py[0] = raw.py[0]; dst.py[1] = raw.py[1];
+    dst.g[0] = raw.g[0] * invlam; dst.g[1] = raw.g[1] * invlam;           // g / lambda (:124)
+}
+
+// One generic iteration of the march: honours all row flags, any nlev <= T.
+template <int T, bool EDGE, bool PIPE>
+__device__ __forceinline__ void cm_generic_iter(int r, CmLv (&h)[T], CmPk (&inbox)[T], CmPk& nxt, double (&err)[T],
                                                 const double* __restrict__ g, const double* __restrict__ pxi,
                                                 const double* __restrict__ pyi, double* __restrict__ pxo,
                                                 double* __restrict__ pyo, int nx, int ny, int j0, int jlast,
-                                                int r0, int rend, long long ibase, const CmLane& L,
+                                                int r0, long long ibase, const CmLane& L,
                                                 double invlam, double tau, int nlev) {
-    CmPk p = nxt;
-    if (r + 1 <= min(rend, ny - 1))
-        cm_load<EDGE>(nxt, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L, invlam);
-    bool live = true;
+    constexpr int D = PIPE ? 2 : 1;
+    CmPk loc[T];                                    // PIPE = false: rows only travel within the iteration
+#define CM_BOX(s_) (PIPE ? inbox[s_] : loc[s_])
 #pragma unroll
-    for (int s = 0; s < T; ++s) {
-        const int jj = r - s;                       // row this level receives
-        if (live && jj >= r0 && jj <= ny) {
+    for (int q = 0; q < T; ++q) {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) { loc[q].px[v] = 0.0; loc[q].py[v] = 0.0; loc[q].g[v] = 0.0; }
+    }
+    cm_take(CM_BOX(0), nxt, invlam);
+    if (r + 1 <= min(jlast + nlev, ny - 1))
+        cm_load<EDGE>(nxt, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L);
+#pragma unroll
+    for (int q = 0; q < T; ++q) {
+        const int s = PIPE ? T - 1 - q : q;
+        const int jj = r - D * s;                   // row this level receives
+        const int need = jlast + nlev - s;          // last row this level has to receive
+        if (s < nlev && jj >= r0 && jj <= min(need, ny)) {
             const bool virt = (jj == ny), last = (jj == ny - 1), first = (jj == r0);
             const int hr = jj - 1;                  // row being updated by this level
             double e = 0.0;
+            CmPk p = CM_BOX(s);
             // first row of a level: nothing held yet -> only u of that row is formed (with the
             // "row above" = 0, exact at the image top); the emitted row is meaningless
             cm_step<EDGE, true>(h[s], p, L, tau, e, virt, last, true);
-            if (first) {
-                live = false;
-            } else {
-                if (hr >= j0 && hr <= jlast) err[s] += e;
+            if (!first) {
+                const bool inseg = hr >= j0 && hr <= jlast;
+                if (inseg) err[s] += e;
                 if (s + 1 == nlev) {
-                    if (hr >= j0 && hr <= jlast)
-                        cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)hr * nx + ibase), L);
-                    live = false;
+                    if (inseg) cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)hr * nx + ibase), L);
+                } else if (s + 1 < T) {
+                    CM_BOX(s + 1) = p;
                 }
             }
-        } else if (jj < r0) {
-            live = false;                           // level (and all above) not started yet
         }
-        // jj > ny: this level is finished; a higher one may still be working
     }
 }
 
 // The march of one warp.  nlev <= T levels are applied.
-template <int T, bool EDGE>
+template <int T, bool EDGE, bool PIPE>
 __device__ __forceinline__ void cm_march(const double* __restrict__ g, const double* __restrict__ pxi,
                                          const double* __restrict__ pyi, double* __restrict__ pxo,
                                          double* __restrict__ pyo, int nx, int ny, int j0, int j1,
                                          const CmLane& L, double invlam, double tau, int nlev,
                                          double (&err)[T]) {
+    constexpr int D = PIPE ? 2 : 1;
     CmLv h[T];
+    CmPk inbox[T];
 #pragma unroll
     for (int s = 0; s < T; ++s) {
 #pragma unroll
-        for (int v = 0; v < 2; ++v) { h[s].px[v] = 0.0; h[s].py[v] = 0.0; h[s].u[v] = 0.0; h[s].g[v] = 0.0; }
+        for (int v = 0; v < 2; ++v) {
+            h[s].px[v] = 0.0; h[s].py[v] = 0.0; h[s].u[v] = 0.0; h[s].g[v] = 0.0;
+            inbox[s].px[v] = 0.0; inbox[s].py[v] = 0.0; inbox[s].g[v] = 0.0;
+        }
     }
     const int r0 = max(j0 - nlev, 0);
     const int jlast = min(j1 - 1, ny - 1);          // last output row of this segment
-    const int rend = jlast + nlev;                  // last step
+    const int rend = jlast + D * (nlev - 1) + 1;    // last iteration (level nlev-1 receives row jlast+1)
     const long long ibase = L.i;
     CmPk nxt;
-    cm_load<EDGE>(nxt, g, pxi, pyi, (size_t)((long long)r0 * nx + ibase), L, invlam);
+    cm_load<EDGE>(nxt, g, pxi, pyi, (size_t)((long long)r0 * nx + ibase), L);
 
     int r = r0;
     if (nlev == T) {
-        const int fast_lo = j0 + T, fast_hi = min(j1, ny - 2);
+        // steady state: every level live, interior rows only, every updated row inside the segment
+        const int fast_lo = j0 + D * (T - 1) + 1, fast_hi = min(j1, ny - 2);
         for (; r < min(fast_lo, rend + 1); ++r)
-            cm_generic_iter<T, EDGE>(r, h, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, rend, ibase, L, invlam, tau, nlev);
-        for (; r <= fast_hi; ++r) {                 // steady state: every level live, no row flags
-            CmPk p = nxt;
-            cm_load<EDGE>(nxt, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L, invlam);
+            cm_generic_iter<T, EDGE, PIPE>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev);
+        for (; r <= fast_hi; ++r) {
+            CmPk loc[T];
+            cm_take(CM_BOX(0), nxt, invlam);
+            cm_load<EDGE>(nxt, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L);
 #pragma unroll
-            for (int s = 0; s < T; ++s) cm_step<EDGE, false>(h[s], p, L, tau, err[s], false, false, true);
-            cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)(r - T) * nx + ibase), L);
+            for (int q = 0; q < T; ++q) {
+                const int s = PIPE ? T - 1 - q : q;
+                CmPk p = CM_BOX(s);
+                cm_step<EDGE, false>(h[s], p, L, tau, err[s], false, false, true);
+                if (s == T - 1) cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)(r - D * (T - 1) - 1) * nx + ibase), L);
+                else CM_BOX(s + 1) = p;
+            }
         }
     }
     for (; r <= rend; ++r)
-        cm_generic_iter<T, EDGE>(r, h, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, rend, ibase, L, invlam, tau, nlev);
+        cm_generic_iter<T, EDGE, PIPE>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev);
 }
 
 // grid = (ceil(nstrips / TV_WARPS), nsegs, batch); block = TV_THREADS.
 // redo == 0: main launch of a block of T sweeps; redo == 1: re-run with the
 // number of levels the stop test asked for (no-op unless st.redo != 0).
-template <int T>
-__global__ void __launch_bounds__(TV_THREADS)
+template <int T, bool PIPE, int MINB>
+__global__ void __launch_bounds__(TV_THREADS, MINB)
 k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, const double* __restrict__ pyi,
               double* __restrict__ pxo, double* __restrict__ pyo, int nx, int ny, int seg, int nstrips,
               size_t img_stride, const Control* __restrict__ ctl, ChambState* __restrict__ st,
@@ -258,8 +289,8 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
         L.central = cen && (L.in0 || L.in1);
         const int j0 = blockIdx.y * seg, j1 = min(j0 + seg, ny);
         const bool edge = (i0 < 0) || (i0 + 64 > nx);
-        if (edge) cm_march<T, true>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
-        else      cm_march<T, false>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
+        if (edge) cm_march<T, true, PIPE>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
+        else      cm_march<T, false, PIPE>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
     }
 
     block_sum<T>(err, sm);
