@@ -168,7 +168,7 @@ void set_geometry(sbd_ctx* c, int batch) {
         int T = 4;
         if (const char* e = getenv("SBD_CHAMB_T")) T = atoi(e);
         if (nx % 2 != 0 || nx < 8) T = 1;           // pairs of pixels must be 16-byte aligned
-        if (const char* e = getenv("SBD_CHAMB_MINB")) c->cm_minb = atoi(e);
+        if (const char* e = getenv("SBD_CHAMB_PIPE")) c->cm_pipe = atoi(e) != 0;
         c->cmT = (T == 3 || T == 4 || T == 5) ? T : 1;
         const int HL = (c->cmT + 1) & ~1, WO = 64 - 2 * HL;
         c->cm_strips = (nx + WO - 1) / WO;
@@ -266,15 +266,26 @@ void tvnorm(sbd_ctx* c, const double* x, double* out, int out_stride, int batch)
 // prox with the options stored in ctl (prox_lambda_theta, tau, tol, maxiter).
 // `maxiter` is the host copy used to size the launch sequence.  The dual pair
 // starts from px0/py0 (caller zeroes or fills them).
-template <int T, int MINB>
-void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const double* pyi, double* pxo,
-                        double* pyo, int batch, int redo) {
-    dim3 grid(c->cm_gx, c->cm_gy, batch);
-    k_chamb_multi<T, false, MINB><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
-                                                                       c->cm_strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
+void zero_duals(sbd_ctx* c, int batch) {
+    SBD_CUDA(cudaMemsetAsync(c->px0, 0, sizeof(double) * batch * c->npix, c->stream));
+    SBD_CUDA(cudaMemsetAsync(c->py0, 0, sizeof(double) * batch * c->npix, c->stream));
 }
 
-void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter) {
+template <int T, bool PIPE, int MINB>
+void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const double* pyi, double* pxo,
+                        double* pyo, int batch, int redo, int zero_in) {
+    dim3 grid(c->cm_gx, c->cm_gy, batch);
+    if (zero_in)
+        k_chamb_multi<T, PIPE, MINB, true><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
+                                                                                c->cm_strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
+    else
+        k_chamb_multi<T, PIPE, MINB, false><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
+                                                                                 c->cm_strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
+}
+
+// zero_start: the dual pair starts from zero (px0/py0 are then neither read nor need to be cleared
+// when the fused kernel runs; the single-sweep path clears them itself)
+void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, bool zero_start) {
     k_chamb_reset<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->chst, batch);
     LAUNCH_CHECK(c);
     dim3 grid(c->tv_gx, c->tv_gy, batch);
@@ -289,22 +300,15 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter) {
             double* pxo = (b & 1) ? c->px0 : c->px1;
             double* pyo = (b & 1) ? c->py0 : c->py1;
             for (int redo = 0; redo < 2; ++redo) {
-                const int mb = c->cm_minb;
-                if (T == 3) {
-                    if (mb == 5) chamb_multi_launch<3, 5>(c, g, pxi, pyi, pxo, pyo, batch, redo);
-                    else if (mb == 4) chamb_multi_launch<3, 4>(c, g, pxi, pyi, pxo, pyo, batch, redo);
-                    else chamb_multi_launch<3, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo);
-                } else if (T == 4) {
-                    if (mb == 4) chamb_multi_launch<4, 4>(c, g, pxi, pyi, pxo, pyo, batch, redo);
-                    else chamb_multi_launch<4, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo);
-                } else {
-                    if (mb == 3) chamb_multi_launch<5, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo);
-                    else chamb_multi_launch<5, 2>(c, g, pxi, pyi, pxo, pyo, batch, redo);
-                }
+                const int zin = (zero_start && b == 0) ? 1 : 0;
+                if (T == 3) chamb_multi_launch<3, false, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
+                else if (T == 5) chamb_multi_launch<5, false, 2>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
+                else chamb_multi_launch<4, false, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
                 LAUNCH_CHECK(c);
             }
         }
     } else {
+        if (zero_start) zero_duals(c, batch);
         for (int s = 0; s < maxiter; ++s) {
             const double* pxi = (s & 1) ? c->px1 : c->px0;
             const double* pyi = (s & 1) ? c->py1 : c->py0;
@@ -323,11 +327,6 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter) {
     else
         k_chamb_out<1><<<grid, TV_THREADS, 0, c->stream>>>(g, c->px0, c->py0, c->px1, c->py1, f, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst);
     LAUNCH_CHECK(c);
-}
-
-void zero_duals(sbd_ctx* c, int batch) {
-    SBD_CUDA(cudaMemsetAsync(c->px0, 0, sizeof(double) * batch * c->npix, c->stream));
-    SBD_CUDA(cudaMemsetAsync(c->py0, 0, sizeof(double) * batch * c->npix, c->stream));
 }
 
 template <typename K>
@@ -664,8 +663,7 @@ int sbd_tvprox_dev(sbd_ctx* c, const double* d_g, double lambda, int maxiter, do
     SBD_CUDA(cudaSetDevice(c->device));
     ensure_ws(c, batch);
     set_chamb_options(c, lambda, maxiter, tol, tau);
-    zero_duals(c, batch);
-    chambolle(c, d_g, d_f, batch, maxiter);
+    chambolle(c, d_g, d_f, batch, maxiter, true);
     fetch_chamb_state(c, batch, iters, err);
     SBD_CATCH(c)
 }
@@ -687,10 +685,8 @@ int sbd_tvprox(sbd_ctx* c, const double* g, double lambda, int maxiter, double t
     if (dual_px) {
         SBD_CUDA(cudaMemcpyAsync(c->px0, dual_px, bytes, cudaMemcpyHostToDevice, c->stream));
         SBD_CUDA(cudaMemcpyAsync(c->py0, dual_py, bytes, cudaMemcpyHostToDevice, c->stream));
-    } else {
-        zero_duals(c, batch);
     }
-    chambolle(c, c->X, c->P, batch, maxiter);
+    chambolle(c, c->X, c->P, batch, maxiter, dual_px == nullptr);
     SBD_CUDA(cudaMemcpyAsync(f, c->P, bytes, cudaMemcpyDeviceToHost, c->stream));
     std::vector<ChambState> h(batch);
     SBD_CUDA(cudaMemcpyAsync(h.data(), c->chst, sizeof(ChambState) * batch, cudaMemcpyDeviceToHost, c->stream));
@@ -923,8 +919,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     const double* gstats = nullptr;
     auto prox = [&]() {
         PhaseTimer pt(c, 3);
-        zero_duals(c, nch);                                        // chambolle_prox_TV_stop.m:68-69
-        chambolle(c, c->X, c->P, nch, prm->chambolle_maxiter);
+        chambolle(c, c->X, c->P, nch, prm->chambolle_maxiter, true);    // zero start: chambolle_prox_TV_stop.m:68-69
     };
     auto myula_step = [&]() {
         { PhaseTimer pt(c, 0);

@@ -43,10 +43,8 @@ __device__ __forceinline__ void fast_sqrt_rcp(double a, double tau, double& tmp,
     const double d = fma(tau, g, 1.0);
     double e = fma(-d, rs, 1.0);
     rs = fma(rs, e, rs);
-    e = fma(-d, rs, 1.0);
-    rs = fma(rs, e, rs);
-    e = fma(-d, rs, 1.0);           // third step: the seed saw d only to ~2^-20
-    rs = fma(rs, e, rs);
+    e = fma(-d, rs, 1.0);           // the seed is 1/d to ~2^-19 (seed error + d known to 2^-20):
+    rs = fma(rs, e, rs);            // two Newton steps reach 2^-38 and 2^-76
     tmp = g; rinv = rs;
 }
 
@@ -112,11 +110,98 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
     p = o;
 }
 
-template <bool EDGE>
+// G independent level steps in lockstep (fast path, PIPE schedule only): the same
+// arithmetic as cm_step<EDGE,false>, written operation by operation across the
+// 2*G pixel chains so that consecutive fp64 instructions are independent.  The
+// fp64 pipe of B200 only reaches ~60% of its rate on a dependent stream, ~85%
+// with four independent chains (tools/fp64_microbench.cu).
+template <bool EDGE, int G>
+__device__ __forceinline__ void cm_step_group(CmLv* h, CmPk* p, const CmLane& L, double tau, double* err) {
+    double un[G][2], upx[G][2], upy[G][2], s2[G][2], gg[G][2], hh[G][2], rs[G][2], rr[G][2];
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+        const double pxl = shfl_up_d(p[s].px[1], 1);
+        double ux0 = p[s].px[0] - pxl, ux1 = p[s].px[1] - p[s].px[0];
+        if (EDGE) {
+            if (L.last0) ux0 = -p[s].px[0];
+            if (L.last1) ux1 = -p[s].px[1];
+        }
+        un[s][0] = ((p[s].py[0] - h[s].py[0]) + ux0) - p[s].g[0];
+        un[s][1] = ((p[s].py[1] - h[s].py[1]) + ux1) - p[s].g[1];
+    }
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+        const double ur = shfl_down_d(h[s].u[0], 1);
+        upx[s][0] = h[s].u[1] - h[s].u[0]; upx[s][1] = ur - h[s].u[1];
+        if (EDGE) {
+            if (L.last0) upx[s][0] = 0.0;
+            if (L.last1) upx[s][1] = 0.0;
+        }
+    }
+#define CM_ALL for (int s = 0; s < G; ++s) for (int v = 0; v < 2; ++v)
+#pragma unroll
+    CM_ALL upy[s][v] = un[s][v] - h[s].u[v];
+#pragma unroll
+    CM_ALL s2[s][v] = fma(upx[s][v], upx[s][v], upy[s][v] * upy[s][v]);
+#pragma unroll
+    CM_ALL { const double y = fast_rsqrt_seed(s2[s][v] + 1e-300); gg[s][v] = s2[s][v] * y; hh[s][v] = 0.5 * y; }
+#pragma unroll
+    CM_ALL rs[s][v] = fast_rcp_seed(fma(tau, gg[s][v], 1.0));
+#pragma unroll
+    CM_ALL rr[s][v] = fma(-gg[s][v], hh[s][v], 0.5);
+#pragma unroll
+    CM_ALL { gg[s][v] = fma(gg[s][v], rr[s][v], gg[s][v]); hh[s][v] = fma(hh[s][v], rr[s][v], hh[s][v]); }
+#pragma unroll
+    CM_ALL rr[s][v] = fma(-gg[s][v], hh[s][v], 0.5);
+#pragma unroll
+    CM_ALL gg[s][v] = fma(gg[s][v], rr[s][v], gg[s][v]);                 // tmp = |grad u|   (:127)
+#pragma unroll
+    CM_ALL hh[s][v] = fma(tau, gg[s][v], 1.0);                           // d = 1 + tau*tmp
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+        CM_ALL rr[s][v] = fma(-hh[s][v], rs[s][v], 1.0);
+#pragma unroll
+        CM_ALL rs[s][v] = fma(rs[s][v], rr[s][v], rs[s][v]);             // 1/d
+    }
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+        double e = 0.0;
+        CmPk o;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const double ex = fma(gg[s][v], h[s].px[v], -upx[s][v]), ey = fma(gg[s][v], h[s].py[v], -upy[s][v]);
+            e += fma(ex, ex, ey * ey);                                   // :128
+            o.px[v] = fma(tau, upx[s][v], h[s].px[v]) * rs[s][v];        // :129
+            o.py[v] = fma(tau, upy[s][v], h[s].py[v]) * rs[s][v];        // :130
+            o.g[v] = h[s].g[v];
+        }
+        if (EDGE) {
+            if (!L.in0) { o.px[0] = 0.0; o.py[0] = 0.0; }
+            if (!L.in1) { o.px[1] = 0.0; o.py[1] = 0.0; }
+        }
+        err[s] += L.central ? e : 0.0;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) { h[s].px[v] = p[s].px[v]; h[s].py[v] = p[s].py[v]; h[s].u[v] = un[s][v]; h[s].g[v] = p[s].g[v]; }
+        p[s] = o;
+    }
+#undef CM_ALL
+}
+
+// ZERO: the incoming dual pair is identically zero (chambolle_prox_TV_stop.m:68-69) and is not loaded
+template <bool EDGE, bool ZERO>
 __device__ __forceinline__ void cm_load(CmPk& p, const double* __restrict__ g, const double* __restrict__ px,
                                         const double* __restrict__ py, size_t off, const CmLane& L) {
     // raw values only: nothing here may depend on the loaded data, or the prefetch would stall
-    if (!EDGE) {
+    if (ZERO) {
+        p.px[0] = 0.0; p.px[1] = 0.0; p.py[0] = 0.0; p.py[1] = 0.0;
+        if (!EDGE) {
+            const double2 c = __ldg(reinterpret_cast<const double2*>(g + off));
+            p.g[0] = c.x; p.g[1] = c.y;
+        } else {
+            p.g[0] = L.in0 ? __ldg(g + off) : 0.0;    p.g[1] = L.in1 ? __ldg(g + off + 1) : 0.0;
+        }
+    } else if (!EDGE) {
         const double2 a = __ldg(reinterpret_cast<const double2*>(px + off));
         const double2 b = __ldg(reinterpret_cast<const double2*>(py + off));
         const double2 c = __ldg(reinterpret_cast<const double2*>(g + off));
@@ -154,7 +239,7 @@ __device__ __forceinline__ void cm_take(CmPk& dst, const CmPk& raw, double invla
 }
 
 // One generic iteration of the march: honours all row flags, any nlev <= T.
-template <int T, bool EDGE, bool PIPE>
+template <int T, bool EDGE, bool PIPE, bool ZERO>
 __device__ __forceinline__ void cm_generic_iter(int r, CmLv (&h)[T], CmPk (&inbox)[T], CmPk& nxt, double (&err)[T],
                                                 const double* __restrict__ g, const double* __restrict__ pxi,
                                                 const double* __restrict__ pyi, double* __restrict__ pxo,
@@ -171,7 +256,7 @@ __device__ __forceinline__ void cm_generic_iter(int r, CmLv (&h)[T], CmPk (&inbo
     }
     cm_take(CM_BOX(0), nxt, invlam);
     if (r + 1 <= min(jlast + nlev, ny - 1))
-        cm_load<EDGE>(nxt, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L);
+        cm_load<EDGE, ZERO>(nxt, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L);
 #pragma unroll
     for (int q = 0; q < T; ++q) {
         const int s = PIPE ? T - 1 - q : q;
@@ -199,7 +284,7 @@ __device__ __forceinline__ void cm_generic_iter(int r, CmLv (&h)[T], CmPk (&inbo
 }
 
 // The march of one warp.  nlev <= T levels are applied.
-template <int T, bool EDGE, bool PIPE>
+template <int T, bool EDGE, bool PIPE, bool ZERO>
 __device__ __forceinline__ void cm_march(const double* __restrict__ g, const double* __restrict__ pxi,
                                          const double* __restrict__ pyi, double* __restrict__ pxo,
                                          double* __restrict__ pyo, int nx, int ny, int j0, int j1,
@@ -221,36 +306,62 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
     const int rend = jlast + D * (nlev - 1) + 1;    // last iteration (level nlev-1 receives row jlast+1)
     const long long ibase = L.i;
     CmPk nxt;
-    cm_load<EDGE>(nxt, g, pxi, pyi, (size_t)((long long)r0 * nx + ibase), L);
+    cm_load<EDGE, ZERO>(nxt, g, pxi, pyi, (size_t)((long long)r0 * nx + ibase), L);
 
     int r = r0;
     if (nlev == T) {
         // steady state: every level live, interior rows only, every updated row inside the segment
         const int fast_lo = j0 + D * (T - 1) + 1, fast_hi = min(j1, ny - 2);
         for (; r < min(fast_lo, rend + 1); ++r)
-            cm_generic_iter<T, EDGE, PIPE>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev);
-        for (; r <= fast_hi; ++r) {
+            cm_generic_iter<T, EDGE, PIPE, ZERO>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev);
+        // Two rows per trip with two named prefetch buffers: the row loaded during one half is
+        // first touched in the next half, a full level-sweep later, and no register rotation
+        // (which the compiler would schedule right behind the load) is needed.
+        auto fast_body = [&](const CmPk& cur, int rr) {
             CmPk loc[T];
-            cm_take(CM_BOX(0), nxt, invlam);
-            cm_load<EDGE>(nxt, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L);
+            cm_take(CM_BOX(0), cur, invlam);
+            if constexpr (PIPE) {
+                // all T levels are independent within the iteration: run them in lockstep groups
+                constexpr int G = (T % 2 == 0) ? 2 : T;
+                CmPk pk[T];
 #pragma unroll
-            for (int q = 0; q < T; ++q) {
-                const int s = PIPE ? T - 1 - q : q;
-                CmPk p = CM_BOX(s);
-                cm_step<EDGE, false>(h[s], p, L, tau, err[s], false, false, true);
-                if (s == T - 1) cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)(r - D * (T - 1) - 1) * nx + ibase), L);
-                else CM_BOX(s + 1) = p;
+                for (int s = 0; s < T; ++s) pk[s] = inbox[s];
+#pragma unroll
+                for (int s0 = 0; s0 < T; s0 += G) cm_step_group<EDGE, G>(&h[s0], &pk[s0], L, tau, &err[s0]);
+                cm_store<EDGE>(pk[T - 1], pxo, pyo, (size_t)((long long)(rr - D * (T - 1) - 1) * nx + ibase), L);
+#pragma unroll
+                for (int s = 0; s + 1 < T; ++s) inbox[s + 1] = pk[s];
+            } else {
+#pragma unroll
+                for (int q = 0; q < T; ++q) {
+                    const int s = q;
+                    CmPk p = CM_BOX(s);
+                    cm_step<EDGE, false>(h[s], p, L, tau, err[s], false, false, true);
+                    if (s == T - 1) cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)(rr - D * (T - 1) - 1) * nx + ibase), L);
+                    else CM_BOX(s + 1) = p;
+                }
             }
+        };
+        if (r <= fast_hi) {
+            CmPk nA = nxt, nB;
+            while (r + 1 <= fast_hi) {
+                cm_load<EDGE, ZERO>(nB, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L);
+                fast_body(nA, r);
+                cm_load<EDGE, ZERO>(nA, g, pxi, pyi, (size_t)((long long)(r + 2) * nx + ibase), L);
+                fast_body(nB, r + 1);
+                r += 2;
+            }
+            nxt = nA;                               // row r, for the generic iterations that follow
         }
     }
     for (; r <= rend; ++r)
-        cm_generic_iter<T, EDGE, PIPE>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev);
+        cm_generic_iter<T, EDGE, PIPE, ZERO>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev);
 }
 
 // grid = (ceil(nstrips / TV_WARPS), nsegs, batch); block = TV_THREADS.
 // redo == 0: main launch of a block of T sweeps; redo == 1: re-run with the
 // number of levels the stop test asked for (no-op unless st.redo != 0).
-template <int T, bool PIPE, int MINB>
+template <int T, bool PIPE, int MINB, bool ZERO>
 __global__ void __launch_bounds__(TV_THREADS, MINB)
 k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, const double* __restrict__ pyi,
               double* __restrict__ pxo, double* __restrict__ pyo, int nx, int ny, int seg, int nstrips,
@@ -289,8 +400,8 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
         L.central = cen && (L.in0 || L.in1);
         const int j0 = blockIdx.y * seg, j1 = min(j0 + seg, ny);
         const bool edge = (i0 < 0) || (i0 + 64 > nx);
-        if (edge) cm_march<T, true, PIPE>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
-        else      cm_march<T, false, PIPE>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
+        if (edge) cm_march<T, true, PIPE, ZERO>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
+        else      cm_march<T, false, PIPE, ZERO>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
     }
 
     block_sum<T>(err, sm);

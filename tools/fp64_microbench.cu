@@ -1,0 +1,52 @@
+// fp64 pipe microbenchmark (B200): DFMA / DADD / DMUL throughput per SM and dependent latency.
+// nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o fp64_microbench fp64_microbench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int ILP, int OP>
+__global__ void k_tp(double* out, int iters, double a, double b) {
+    double v[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) v[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            if (OP == 0) v[i] = fma(v[i], a, b);
+            else if (OP == 1) v[i] = v[i] + a;
+            else v[i] = v[i] * a;
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += v[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int ILP, int OP>
+void run(const char* name, int warps_per_sm) {
+    int dev; cudaGetDevice(&dev);
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, dev);
+    const int threads = 128, blocks = p.multiProcessorCount * warps_per_sm / 4;
+    double* out; cudaMalloc(&out, sizeof(double) * threads * blocks);
+    const int iters = 20000;
+    k_tp<ILP, OP><<<blocks, threads>>>(out, 100, 1.0000001, 1e-9);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    k_tp<ILP, OP><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
+    const double ops = (double)blocks * threads * iters * ILP;
+    const double per_clk_sm = ops / (ms * 1e-3) / (clk * 1e3) / p.multiProcessorCount;
+    printf("%-6s ILP=%d warps/SM=%2d : %.3f ms  %.1f Gop/s  %.1f lanes/clk/SM (at %d MHz nominal)\n", name, ILP,
+           warps_per_sm, ms, ops / ms * 1e-6, per_clk_sm, clk / 1000);
+    cudaFree(out);
+}
+
+int main() {
+    run<1, 0>("DFMA", 4);  run<1, 0>("DFMA", 8);  run<1, 0>("DFMA", 16); run<1, 0>("DFMA", 32); run<1, 0>("DFMA", 64);
+    run<2, 0>("DFMA", 8);  run<2, 0>("DFMA", 12); run<2, 0>("DFMA", 16);
+    run<4, 0>("DFMA", 4);  run<4, 0>("DFMA", 8);  run<4, 0>("DFMA", 16); run<8, 0>("DFMA", 16); run<8, 0>("DFMA", 32);
+    run<8, 1>("DADD", 16); run<8, 2>("DMUL", 16);
+    return 0;
+}
