@@ -1,0 +1,140 @@
+"""GPU parity against the golden fixtures produced by EXECUTING THE REFERENCE'S
+OWN .m FILES (tests/golden/make_golden.py): the CUDA engine, through the C ABI,
+versus the reference itself - operators to 1e-12, SAPG trajectories to 1e-6
+(BASELINE.json north_star tolerances)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel, GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+TRAJ_TOL = 1e-6
+
+
+def sc(v):
+    return float(np.asarray(v).ravel()[0])
+
+
+@pytest.fixture(scope="module")
+def sbd():
+    import sbd_b200
+    return sbd_b200
+
+
+@pytest.fixture(scope="module")
+def G():
+    return dict(np.load(os.path.join(GOLDEN, "ref_operators.npz")))
+
+
+def test_psf_builders_vs_reference(sbd, G):
+    assert rel(sbd.Gaussian_psf(7, 0.4, 0.3, 0.0), G["gauss_psf"]) < TOL
+    assert rel(sbd.psf_gaussian(7, 0.5, 0.2, 0.3), G["gauss_psf_rot"]) < TOL
+    assert rel(sbd.gaussian_fft((16, 32), 7, 0.4, 0.3, 0.0), G["gauss_H"]) < TOL
+    assert rel(sbd.diff_fftgaus_w1((16, 32), 7, 0.4, 0.3, 0.0), G["gauss_dw1"]) < TOL
+    assert rel(sbd.diff_fftgaus_w2((16, 32), 7, 0.4, 0.3, 0.0), G["gauss_dw2"]) < TOL
+    assert rel(sbd.psf_moffat(7, 0.4, 3.5), G["moffat_psf"]) < TOL
+    assert rel(sbd.moffat_psf((16, 32), 7, 0.4, 3.5), G["moffat_H"]) < TOL
+    assert rel(sbd.diff_moffat_alpha((16, 32), 7, 0.4, 3.5), G["moffat_da"]) < TOL
+    assert rel(sbd.diff_moffat_beta((16, 32), 7, 0.4, 3.5), G["moffat_db"]) < TOL
+    assert rel(sbd.psf_laplace(7, 0.3), G["laplace_psf"]) < TOL
+    assert rel(sbd.laplace_psf((16, 32), 7, 0.3), G["laplace_H"]) < TOL
+    assert rel(sbd.diff_laplace_b((16, 32), 7, 0.3), G["laplace_db"]) < TOL
+
+
+def test_tv_pieces_vs_reference(sbd, G):
+    x = G["tv_x"]
+    assert abs(sbd.TVnorm(x) - sc(G["tvnorm"])) <= TOL * sc(G["tvnorm"])
+    assert np.array_equal(sbd.diffh(x), G["diffh"]) and np.array_equal(sbd.diffv(x), G["diffv"])
+    for i in range(3):
+        f, px, py = sbd.chambolle_prox_TV_stop(x, "lambda", sc(G[f"chamb{i}_lambda"]), "maxiter", 25)
+        assert rel(f, G[f"chamb{i}_f"]) < TOL
+        assert rel(px, G[f"chamb{i}_px"]) < 1e-11 and rel(py, G[f"chamb{i}_py"]) < 1e-11
+    f, px, py = sbd.chambolle_prox_TV_stop(G["chamb_opt_g"], "LAMBDA", 0.7, "MaxIter", 10, "tol", 1e-2, "tau", 0.2,
+                                           "dualvars", G["chamb_opt_dual"])
+    assert rel(f, G["chamb_opt_f"]) < TOL and rel(px, G["chamb_opt_px"]) < 1e-11 and rel(py, G["chamb_opt_py"]) < 1e-11
+
+
+MODELS = {"gaussian": 0, "moffat": 1, "laplace": 2}
+PROBE_PSI = {"gaussian": (0.5, 0.35), "moffat": (0.8, 6.0), "laplace": (0.15,)}
+
+
+def build_op(name, g):
+    """`op` as the demo script leaves it: hyper-parameters of the script + the
+    values the reference execution computed (sigma's, lambda, gamma)."""
+    from oracle.operators import DEFAULTS, C_GAUSSIAN
+    op = dict(DEFAULTS[MODELS[name]])
+    op.update(samples=16, warmup=6, burnIn=12, d_scale=0.01 / op["th_init"], x=g["x"])
+    if name == "gaussian":
+        op.update(fix_w1=0, fix_w2=0)
+    for k in ("sigma", "sigma_init", "sigma_min", "sigma_max", "lambda", "gamma"):
+        op[k] = sc(g["op_" + k])
+    if name == "laplace":
+        op["X0"] = g["y"]
+    return op, dict(C_GAUSSIAN)
+
+
+def noise_tape(g, n):
+    """the draws the SAPG function consumed: the stream continues after the
+    power-iteration start vector and the observation noise"""
+    rng = np.random.default_rng(int(sc(g["seed"])))
+    shape = g["x"].shape
+    rng.standard_normal(shape); rng.standard_normal(shape)
+    return np.stack([rng.standard_normal(shape) for _ in range(n)])[:, None]
+
+
+@pytest.mark.parametrize("name", ["gaussian", "moffat", "laplace"])
+def test_closures_vs_reference(sbd, name):
+    g = dict(np.load(os.path.join(GOLDEN, f"ref_sapg_{name}.npz")))
+    xp, psi, s2, th = g["probe_xp"], PROBE_PSI[name], 7.5, 0.04
+    cl = sbd.host._closures(MODELS[name], xp.shape, 7, 0.0)
+    assert rel(cl["A"](xp, *psi), g["probe_A"]) < TOL
+    assert rel(cl["AT"](xp, *psi), g["probe_AT"]) < TOL
+    got = cl["engine"].likelihood(xp, g["y"], psi, s2, th)
+    assert rel(got["gradF"], g["probe_gradF"]) < TOL
+    assert abs(got["f"] - sc(g["probe_f"])) <= TOL * sc(g["probe_f"])
+    assert abs(got["gradF_sigma"] - sc(g["probe_gradF_sigma"])) <= 1e-11 * abs(sc(g["probe_gradF_sigma"]))
+    assert abs(got["logPi"] - sc(g["probe_logPi"])) <= TOL * abs(sc(g["probe_logPi"]))
+    assert abs(got["g"] - sc(g["probe_g"])) <= TOL * sc(g["probe_g"])
+    for i in range(1 if name == "laplace" else 2):
+        want = sc(g[f"probe_grad_psi{i}"])
+        assert abs(got[f"grad_psi{i}"] - want) <= 1e-9 * (abs(want) + 1.0)
+    lam = sc(g["op_lambda"])
+    f, _, _ = sbd.chambolle_prox_TV_stop(xp, "lambda", lam * th, "maxiter", 25)
+    assert rel(f, g["probe_proxG"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["gaussian", "moffat", "laplace"])
+def test_sapg_vs_reference_execution(sbd, name):
+    g = dict(np.load(os.path.join(GOLDEN, f"ref_sapg_{name}.npz")))
+    op, c = build_op(name, g)
+    noise = noise_tape(g, (6 - 1) + (16 - 1))
+    if name == "gaussian":
+        out = sbd.SAPG_algorithm_Guassian(g["y"], op, c, noise=noise)
+    elif name == "moffat":
+        out = sbd.SAPG_algorithm_moffat(g["y"], op, noise=noise)
+    else:
+        out = sbd.SAPG_algorithm_laplace(g["y"], op, noise=noise)
+    r = out[-1]
+    checked = 0
+    for k, want in g.items():
+        if not k.startswith("res_"):
+            continue
+        f = k[4:]
+        if f.startswith("execTime") or f == "gamma" or f == "lambda":
+            continue
+        assert f in r, f"results lack field {f}"
+        got = np.asarray(r[f], dtype=np.float64)
+        want = np.asarray(want, dtype=np.float64)
+        assert got.size == want.size, (f, got.shape, want.shape)
+        got = got.reshape(want.shape)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), f
+        m = ~np.isnan(want)
+        if f.startswith("tol_"):
+            assert np.allclose(got[m], want[m], rtol=1e-4, atol=1e-14), f
+        else:
+            assert rel(got[m], want[m]) < TRAJ_TOL, (f, rel(got[m], want[m]))
+        checked += 1
+    assert checked >= 25
