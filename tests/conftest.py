@@ -17,7 +17,9 @@ def pytest_configure(config):
 
 def rel(a, b):
     """||a-b||_2 / ||b||_2 for arrays, |a-b|/|b| for scalars (SURVEY.md 7.1 parity metric)."""
-    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    a = np.asarray(a); b = np.asarray(b)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = a.astype(dt); b = b.astype(dt)
     den = np.linalg.norm(b.ravel())
     num = np.linalg.norm((a - b).ravel())
     return num / den if den > 0 else num
