@@ -409,6 +409,14 @@ class Parser:
             elif tk.val == "." and self.peek(1).kind == "id" and not tk.sp:
                 self.next()
                 e = ("field", e, self.next().val)
+            elif tk.val == "." and self.peek(1).kind == "op" and self.peek(1).val == "(" and not tk.sp:
+                self.next(); self.next()
+                saved = self.in_matrix
+                self.in_matrix = 0
+                name = self.parse_expr()
+                self.in_matrix = saved
+                self.expect(")")
+                e = ("dynfield", e, name)
             elif tk.val in ("'", ".'"):
                 self.next()
                 e = ("un", tk.val, e)
@@ -458,8 +466,20 @@ class Parser:
             if tk.val == "[":
                 return self.parse_matrix()
             if tk.val == "{":
+                items = []
+                self.in_matrix += 1
+                saved_idx = self.in_index
+                self.in_index = 0
+                try:
+                    while not self.at("}"):
+                        if self.at(",") or self.at(";") or self.peek().kind == "nl":
+                            self.next(); continue
+                        items.append(self.parse_expr())
+                finally:
+                    self.in_matrix -= 1
+                    self.in_index = saved_idx
                 self.expect("}")
-                return ("emptycell",)
+                return ("cellarr", items)
             if tk.val == "@":
                 if self.at("("):
                     self.next()
@@ -941,6 +961,14 @@ class Interp:
             return [self.build_matrix(e[1], scope, local, end_val)]
         if k == "emptycell":
             return [MCell()]
+        if k == "cellarr":
+            return [MCell([self.eval(x, scope, local, end_val) for x in e[1]])]
+        if k == "dynfield":
+            base = self.eval(e[1], scope, local, end_val)
+            name = self.eval(e[2], scope, local, end_val)
+            if not isinstance(base, MStruct) or name not in base:
+                raise MatlabError(f"Reference to non-existent field '{name}'.")
+            return [base[name]]
         if k == "range":
             a = scalar(self.eval(e[1], scope, local, end_val))
             b = scalar(self.eval(e[3], scope, local, end_val))
@@ -1031,7 +1059,12 @@ class Interp:
             return np.zeros((0, 0))
         out_rows = []
         for row in rows:
-            vals = [self.eval(x, scope, local, end_val) for x in row]
+            vals = []
+            for x in row:
+                if x[0] == "cell" and len(x[2]) == 1 and x[2][0][0] == "colon":      # [c{:}]
+                    vals.extend(list(self.eval(x[1], scope, local, end_val)))
+                else:
+                    vals.append(self.eval(x, scope, local, end_val))
             if all(isinstance(v, str) for v in vals):
                 out_rows.append("".join(vals)); continue
             mats = [M(v) for v in vals if not (is_num(v) and M(v).size == 0)]

@@ -1,0 +1,3 @@
+function H = diff_fftgaus_w1(im_shape, taille, w1, w2, phi)
+% Drop-in for utils/diff_fftgaus_w1.m:2-26 (PSF / derivative spectrum = resize(kernel, im_shape)).
+H = sbd_mex('spectrum', double(im_shape(1:2)), 0, taille, phi, [w1 w2], 1);
