@@ -311,7 +311,8 @@ struct ColArgs {
     unsigned int* counters; // [batch]
     double* stats;          // [batch][NSTAT] (rss -> 1, c0 -> 2, c1 -> 3), already divided by nx*ny
     size_t spec_stride;
-    int nk, nxfull, t, npsi, C, logC, opsel;
+    int nk, nxfull, t, npsi, C, logC, opsel;   // C = columns per block
+    int LC, nsub, ntiles;                      // layout tile width, blocks per tile, tiles per image
     double opscale;
 };
 
@@ -322,12 +323,13 @@ __global__ void k_cols(const ColArgs a) {
     __shared__ double redS[3 * 32];
     constexpr int TL = N / 16;
     const int img = blockIdx.y;
-    const int C = a.C;
-    const int k0 = blockIdx.x * C;
-    const size_t tile_off = (size_t)img * a.spec_stride + (size_t)blockIdx.x * N * C;
+    const int C = a.C, LC = a.LC;
+    const int tile = blockIdx.x / a.nsub, sub = blockIdx.x - tile * a.nsub;
+    const int k0 = tile * LC + sub * C;
+    const size_t tile_off = (size_t)img * a.spec_stride + (size_t)tile * N * LC + (size_t)sub * C;
     const double2* in = a.in + tile_off;
     double2* out = a.out + tile_off;
-    const double2* yh = a.yhat + (size_t)blockIdx.x * N * C;
+    const double2* yh = a.yhat + (size_t)tile * N * LC + (size_t)sub * C;
 
     if (MODE != COL_FWD) {
         for (int e = threadIdx.x; e < C * 3 * a.t; e += blockDim.x) {
@@ -346,11 +348,11 @@ __global__ void k_cols(const ColArgs a) {
     double acc[3] = {0.0, 0.0, 0.0};
 
     auto gsrc = [&](int q) {
-        double2 v = __ldg(in + (size_t)q * C + c);
+        double2 v = __ldg(in + (size_t)q * LC + c);
         if (MODE == COL_MUL_INV) {
             const double2 w = __ldg(a.tw + q);
             const double2 H = psf_horner(coefS[c][0], a.t, w);
-            const double2 yv = __ldg(yh + (size_t)q * C + c);
+            const double2 yv = __ldg(yh + (size_t)q * LC + c);
             const double2 R = csub(cmul(H, v), yv);                 // H X^ - Y^
             const double2 G = cmulc(R, H);                          // conj(H) R
             const double sc = a.ctl->inv_scale;
@@ -360,10 +362,10 @@ __global__ void k_cols(const ColArgs a) {
     };
     auto gdst = [&](int q, double2 v) {
         if (!kin) return;
-        out[(size_t)q * C + c] = v;
+        out[(size_t)q * LC + c] = v;
         if (MODE == COL_FWD_REDUCE) {
             const double2 w = __ldg(a.tw + q);
-            const double2 yv = __ldg(yh + (size_t)q * C + c);
+            const double2 yv = __ldg(yh + (size_t)q * LC + c);
             const double2 H = psf_horner(coefS[c][0], a.t, w);
             const double2 R = csub(cmul(H, v), yv);
             // Hermitian weights of the half spectrum: interior bins count twice

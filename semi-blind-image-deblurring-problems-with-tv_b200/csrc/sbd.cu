@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <map>
 
 using namespace sbd;
 
@@ -76,6 +77,7 @@ struct sbd_ctx {
     bool cm_pipe = false;
     int cm_minb = 3;
     int rowsLP = 1, rowsT = 32, colsC = 2, colsLogC = 1, colsT = 32, ntiles = 1;
+    int colsKC = 2, colsLogKC = 1;     // columns per block of the column pass (<= colsC, the layout tile width)
     size_t rows_smem = 0, cols_smem = 0;
     int geom_batch = -1;
 
@@ -188,7 +190,7 @@ void set_geometry(sbd_ctx* c, int batch) {
         c->rowsLP = LP;
         c->rowsT = std::max(32, LP * nx / 16);
         c->rows_smem = (size_t)LP * le_x * 16;
-        c->colsT = std::max(32, c->colsC * ny / 16);
+        c->colsT = std::max(32, c->colsKC * ny / 16);
     }
     c->geom_batch = batch;
 }
@@ -218,7 +220,7 @@ void ensure_ws(sbd_ctx* c, int batch) {
     const size_t maxparts = (size_t)((strips + TV_WARPS - 1) / TV_WARPS) * c->ny;    // seg = 1 bound
     c->part_tv = dalloc<double>((size_t)batch * maxparts);
     c->part_ch = dalloc<double>((size_t)batch * maxparts * 5);     // up to T = 5 levels per launch
-    c->part_col = dalloc<double>((size_t)batch * (c->nk + 1) * 4);
+    c->part_col = dalloc<double>((size_t)batch * (c->nk + 8) * 4);
     c->part_sq = dalloc<double>((size_t)batch * 1024);
     c->ws_batch = batch;
 }
@@ -331,8 +333,14 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
 
 template <typename K>
 void set_smem(K kernel, size_t bytes) {
+    // opt in to > 48 KB of dynamic shared memory, once per (kernel, size)
+    static std::map<const void*, size_t> done;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return;
     if (bytes > 48 * 1024)
         SBD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done[key] = bytes;
 }
 
 #define SBD_FFT_SIZES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
@@ -377,10 +385,11 @@ void cols(sbd_ctx* c, const double2* in, double2* out, int batch, int opsel = 0)
     a.in = in; a.out = out; a.yhat = c->yhat; a.coef = c->coef; a.tw = c->tw_ny; a.ctl = c->ctl;
     a.partials = c->part_col; a.counters = c->cnt_col; a.stats = c->stats;
     a.spec_stride = c->spec_elems; a.nk = c->nk; a.nxfull = c->nx; a.t = c->t;
-    a.npsi = (c->model == SBD_LAPLACE) ? 1 : 2; a.C = c->colsC; a.logC = c->colsLogC; a.opsel = opsel;
+    a.npsi = (c->model == SBD_LAPLACE) ? 1 : 2; a.C = c->colsKC; a.logC = c->colsLogKC; a.LC = c->colsC;
+    a.nsub = c->colsC / c->colsKC; a.ntiles = c->ntiles; a.opsel = opsel;
     a.opscale = 1.0 / ((double)c->nx * (double)c->ny);
     const size_t smem = c->cols_smem;
-    dim3 g(c->ntiles, batch);
+    dim3 g(c->ntiles * (c->colsC / c->colsKC), batch);
     switch (c->ny) {
 #define X(N) case N: set_smem(k_cols<N, MODE>, smem); \
         k_cols<N, MODE><<<g, c->colsT, smem, c->stream>>>(a); break;
@@ -493,7 +502,14 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
             c->colsC = C;
             c->colsLogC = (C == 8) ? 3 : (C == 4) ? 2 : (C == 2) ? 1 : 0;
             c->ntiles = (c->nk + C - 1) / C;
-            c->cols_smem = (size_t)C * le_y * 16;
+            int KC = C;
+            if (const char* e = getenv("SBD_COLS_KC")) {
+                const int v = atoi(e);
+                if ((v == 1 || v == 2 || v == 4 || v == 8) && v <= C) KC = v;
+            }
+            c->colsKC = KC;
+            c->colsLogKC = (KC == 8) ? 3 : (KC == 4) ? 2 : (KC == 2) ? 1 : 0;
+            c->cols_smem = (size_t)KC * le_y * 16;
         }
         c->spec_elems = (size_t)c->ntiles * cols * c->colsC;
         c->profile = getenv("SBD_PROFILE") && atoi(getenv("SBD_PROFILE")) != 0;
@@ -945,13 +961,43 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
         if (mode == 2) psf_refresh_coef(c, c->nk);
     };
 
+    // n iterations of (MYULA step + scalar kernel `mode`).  With use_graph the fixed launch sequence of
+    // one iteration (all scalars are device-resident) is captured once and replayed: at small image
+    // sizes the iteration is launch-bound and the graph removes most of the per-launch CPU cost.
+    auto run_loop = [&](int n, int mode) {
+        if (n <= 0) return;
+        const bool graph = prm->use_graph && !c->profile && n >= 4;
+        if (!graph) {
+            for (int i = 0; i < n; ++i) { myula_step(); scalar(mode); }
+            return;
+        }
+        myula_step(); scalar(mode);                                 // first iteration eagerly (sets kernel attributes)
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        const long long l0 = c->launches;
+        SBD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        try {
+            myula_step(); scalar(mode);
+        } catch (...) {
+            cudaStreamEndCapture(s, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        SBD_CUDA(cudaStreamEndCapture(s, &g));
+        const long long per_iter = c->launches - l0;
+        c->launches = l0;
+        SBD_CUDA(cudaGraphInstantiate(&ge, g, 0));
+        for (int i = 1; i < n; ++i) SBD_CUDA(cudaGraphLaunch(ge, s));
+        c->launches += per_iter * (n - 1);
+        SBD_CUDA(cudaStreamSynchronize(s));
+        cudaGraphExecDestroy(ge);
+        cudaGraphDestroy(g);
+    };
+
     // ---- warm-up (Guassian.m:67-93)
     analyse(c, nch);
     prox();                                                         // :76
-    for (int ii = 2; ii <= warmup; ++ii) {                          // :78
-        myula_step();
-        scalar(1);
-    }
+    run_loop(warmup - 1, 1);                                        // :78  for ii = 2:warmupSteps
     if (out->X_warm)
         SBD_CUDA(cudaMemcpyAsync(out->X_warm, c->X, sizeof(double) * nch * c->npix, cudaMemcpyDeviceToHost, s));
 
@@ -964,10 +1010,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     SBD_CUDA(cudaEventCreate(&evm));
     SBD_CUDA(cudaEventRecord(evm, s));
     const long long launches0 = c->launches;
-    for (int ii = 2; ii <= samples; ++ii) {                         // :158
-        myula_step();
-        scalar(2);
-    }
+    run_loop(samples - 1, 2);                                       // :158  for ii = 2:total_iter
     SBD_CUDA(cudaEventRecord(ev1, s));
     out->launches_main = c->launches - launches0;
     c->profile = false;

@@ -169,3 +169,14 @@ def test_posterior_mean_psnr(sbd, O, cman):
     want = np.mean(np.stack(main[B:S]), axis=0)     # X_ii for ii = B+1 .. S
     assert rel(g["posteriormean"], want) < TRAJ_TOL
     assert abs(O.metrics.PSNR(x, g["posteriormean"]) - O.metrics.PSNR(x, want)) < 0.01
+
+
+def test_sapg_cuda_graph_mode_is_identical(sbd, O, cman):
+    """use_graph replays the captured iteration: trajectories must be bit-identical to eager launches."""
+    x = cman[96:160, 64:128]
+    tape, (y, op, c) = _setup(O, 0, x, samples=24, warmup=9, burnIn=12, fix_w1=0, fix_w2=0)
+    _, _, _, _, a = sbd.SAPG_algorithm_Guassian(y, op, c, n_chains=2, seed=5)
+    _, _, _, _, b = sbd.SAPG_algorithm_Guassian(y, dict(op, use_graph=1), c, n_chains=2, seed=5)
+    for k in ("thetas", "w1s", "w2s", "sigmas", "logPiTraceX", "logPiTrace_WU", "gXTrace", "grad_w1"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["Xlast_sample"], b["Xlast_sample"])
