@@ -176,7 +176,7 @@ void set_geometry(sbd_ctx* c, int batch) {
         c->cm_strips = (nx + WO - 1) / WO;
         c->cm_gx = (c->cm_strips + TV_WARPS - 1) / TV_WARPS;
         int sg = 128;
-        while (sg > 16 && (long long)c->cm_gx * ((ny + sg - 1) / sg) * batch < 6 * 148) sg /= 2;
+        while (sg > 8 && (long long)c->cm_gx * ((ny + sg - 1) / sg) * batch < 6 * 148) sg /= 2;
         if (const char* e = getenv("SBD_CHAMB_SEG")) sg = std::max(1, atoi(e));
         c->cm_seg = sg;
         c->cm_gy = (ny + sg - 1) / sg;
@@ -276,13 +276,16 @@ void zero_duals(sbd_ctx* c, int batch) {
 template <int T, bool PIPE, int MINB>
 void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const double* pyi, double* pxo,
                         double* pyo, int batch, int redo, int zero_in) {
-    dim3 grid(c->cm_gx, c->cm_gy, batch);
+    // strip geometry depends on the number of fused levels (lateral halo HL, 64 - 2*HL outputs per strip)
+    constexpr int HL = (T + 1) & ~1, WO = 64 - 2 * HL;
+    const int strips = (c->nx + WO - 1) / WO;
+    dim3 grid((strips + TV_WARPS - 1) / TV_WARPS, c->cm_gy, batch);
     if (zero_in)
         k_chamb_multi<T, PIPE, MINB, true><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
-                                                                                c->cm_strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
+                                                                                strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
     else
         k_chamb_multi<T, PIPE, MINB, false><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
-                                                                                 c->cm_strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
+                                                                                 strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
 }
 
 // zero_start: the dual pair starts from zero (px0/py0 are then neither read nor need to be cleared
@@ -293,10 +296,24 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
     dim3 grid(c->tv_gx, c->tv_gy, batch);
     PhaseTimer* pt = new PhaseTimer(c, 2);
     if (c->cmT > 1) {
-        // blocks of T fused sweeps; each block = main launch + redo launch (no-op unless the
-        // reference's stop test fired inside the block)
-        const int T = c->cmT, nblk = (maxiter + T - 1) / T;
-        for (int b = 0; b < nblk; ++b) {
+        // blocks of fused sweeps; each block = main launch + redo launch (a no-op unless the reference's
+        // stop test fired inside the block).  Block sizes: as many 4-level blocks as possible, with 5-level
+        // blocks absorbing the remainder (K = 25 -> 5,4,4,4,4,4); a short tail runs the generic path.
+        std::vector<int> plan;
+        if (c->cmT == 4) {
+            const int a = maxiter / 4, r = maxiter % 4;
+            if (a > 0 && r <= a) {
+                for (int i = 0; i < r; ++i) plan.push_back(5);
+                for (int i = 0; i < a - r; ++i) plan.push_back(4);
+            } else {
+                for (int i = 0; i < a; ++i) plan.push_back(4);
+                if (r) plan.push_back(4);           // kernel applies min(4, remaining) levels
+            }
+        } else {
+            for (int k = 0; k < maxiter; k += c->cmT) plan.push_back(c->cmT);
+        }
+        for (size_t b = 0; b < plan.size(); ++b) {
+            const int T = plan[b];
             const double* pxi = (b & 1) ? c->px1 : c->px0;
             const double* pyi = (b & 1) ? c->py1 : c->py0;
             double* pxo = (b & 1) ? c->px0 : c->px1;
