@@ -193,24 +193,16 @@ template <bool EDGE, bool ZERO>
 __device__ __forceinline__ void cm_load(CmPk& p, const double* __restrict__ g, const double* __restrict__ px,
                                         const double* __restrict__ py, size_t off, const CmLane& L) {
     // raw values only: nothing here may depend on the loaded data, or the prefetch would stall
+    // 64-bit loads on purpose: a 128-bit load needs an aligned register quad, and the copies the
+    // register allocator then inserts right behind the load stall on it (ncu: long_scoreboard on a MOV)
     if (ZERO) {
         p.px[0] = 0.0; p.px[1] = 0.0; p.py[0] = 0.0; p.py[1] = 0.0;
-        if (!EDGE) {
-            const double2 c = __ldg(reinterpret_cast<const double2*>(g + off));
-            p.g[0] = c.x; p.g[1] = c.y;
-        } else {
-            p.g[0] = L.in0 ? __ldg(g + off) : 0.0;    p.g[1] = L.in1 ? __ldg(g + off + 1) : 0.0;
-        }
-    } else if (!EDGE) {
-        const double2 a = __ldg(reinterpret_cast<const double2*>(px + off));
-        const double2 b = __ldg(reinterpret_cast<const double2*>(py + off));
-        const double2 c = __ldg(reinterpret_cast<const double2*>(g + off));
-        p.px[0] = a.x; p.px[1] = a.y; p.py[0] = b.x; p.py[1] = b.y;
-        p.g[0] = c.x; p.g[1] = c.y;
+        p.g[0] = (!EDGE || L.in0) ? __ldg(g + off) : 0.0;
+        p.g[1] = (!EDGE || L.in1) ? __ldg(g + off + 1) : 0.0;
     } else {
-        p.px[0] = L.in0 ? __ldg(px + off) : 0.0;      p.px[1] = L.in1 ? __ldg(px + off + 1) : 0.0;
-        p.py[0] = L.in0 ? __ldg(py + off) : 0.0;      p.py[1] = L.in1 ? __ldg(py + off + 1) : 0.0;
-        p.g[0] = L.in0 ? __ldg(g + off) : 0.0;        p.g[1] = L.in1 ? __ldg(g + off + 1) : 0.0;
+        p.px[0] = (!EDGE || L.in0) ? __ldg(px + off) : 0.0;   p.px[1] = (!EDGE || L.in1) ? __ldg(px + off + 1) : 0.0;
+        p.py[0] = (!EDGE || L.in0) ? __ldg(py + off) : 0.0;   p.py[1] = (!EDGE || L.in1) ? __ldg(py + off + 1) : 0.0;
+        p.g[0] = (!EDGE || L.in0) ? __ldg(g + off) : 0.0;     p.g[1] = (!EDGE || L.in1) ? __ldg(g + off + 1) : 0.0;
     }
 }
 
