@@ -137,10 +137,25 @@ __device__ __forceinline__ void stage_load(int tl, double2 (&v)[16], Src src, co
 #pragma unroll
         for (int r = 0; r < R; ++r) v[m * R + r] = src(jb + r * Q);
         if (NS > 1) {
+            // twiddles w^r, w = W_N^(k*STEP): only the powers 1, 2, 4, 8 are fetched from the table, the
+            // rest are products of at most three of them (<= 4 ulp).  Fetching all R-1 costs several
+            // times more LSU wavefronts than moving the data itself (scattered 16-byte table reads).
             const int k = jb & (NS - 1);
             constexpr int STEP = N / (NS * R);
+            double2 w[R];
+            w[1] = twid<INV>(tw, k * STEP);
+            if (R >= 4) { w[2] = twid<INV>(tw, 2 * k * STEP); w[3] = cmul(w[1], w[2]); }
+            if (R >= 8) {
+                w[4] = twid<INV>(tw, 4 * k * STEP);
+                w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]);
+            }
+            if (R >= 16) {
+                w[8] = twid<INV>(tw, 8 * k * STEP);
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[m * R + r] = cmul(v[m * R + r], twid<INV>(tw, r * k * STEP));
+                for (int r = 1; r < 8; ++r) w[8 + r] = cmul(w[r], w[8]);
+            }
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[m * R + r] = cmul(v[m * R + r], w[r]);
         }
         Dft<R, INV>::run(&v[m * R]);
     }

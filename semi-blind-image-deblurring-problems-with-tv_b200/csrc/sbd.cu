@@ -515,15 +515,16 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
                 const int v = atoi(e);
                 if (v == 1 || v == 2 || v == 4 || v == 8) C = v;
             }
-            while (C > 1 && ((size_t)C * cols / 16 > 1024 || (size_t)C * le_y * 16 > 220 * 1024)) C /= 2;
             c->colsC = C;
             c->colsLogC = (C == 8) ? 3 : (C == 4) ? 2 : (C == 2) ? 1 : 0;
             c->ntiles = (c->nk + C - 1) / C;
+            // columns per block (<= tile width): bounded by threads (<= 1024) and shared memory
             int KC = C;
             if (const char* e = getenv("SBD_COLS_KC")) {
                 const int v = atoi(e);
                 if ((v == 1 || v == 2 || v == 4 || v == 8) && v <= C) KC = v;
             }
+            while (KC > 1 && ((size_t)KC * cols / 16 > 1024 || (size_t)KC * le_y * 16 > 220 * 1024)) KC /= 2;
             c->colsKC = KC;
             c->colsLogKC = (KC == 8) ? 3 : (KC == 4) ? 2 : (KC == 2) ? 1 : 0;
             c->cols_smem = (size_t)KC * le_y * 16;
