@@ -40,6 +40,7 @@ __device__ __forceinline__ void fast_sqrt_rcp(double a, double tau, double& tmp,
     g = fma(g, r, g); h = fma(h, r, h);
     r = fma(-g, h, 0.5);
     g = fma(g, r, g);
+    // (one Goldschmidt step + a residual correction needs two fp64 ops fewer but measured 3% slower)
     const double d = fma(tau, g, 1.0);
     double e = fma(-d, rs, 1.0);
     rs = fma(rs, e, rs);
@@ -110,84 +111,6 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
     p = o;
 }
 
-// G independent level steps in lockstep (fast path, PIPE schedule only): the same
-// arithmetic as cm_step<EDGE,false>, written operation by operation across the
-// 2*G pixel chains so that consecutive fp64 instructions are independent.  The
-// fp64 pipe of B200 only reaches ~60% of its rate on a dependent stream, ~85%
-// with four independent chains (tools/fp64_microbench.cu).
-template <bool EDGE, int G>
-__device__ __forceinline__ void cm_step_group(CmLv* h, CmPk* p, const CmLane& L, double tau, double* err) {
-    double un[G][2], upx[G][2], upy[G][2], s2[G][2], gg[G][2], hh[G][2], rs[G][2], rr[G][2];
-#pragma unroll
-    for (int s = 0; s < G; ++s) {
-        const double pxl = shfl_up_d(p[s].px[1], 1);
-        double ux0 = p[s].px[0] - pxl, ux1 = p[s].px[1] - p[s].px[0];
-        if (EDGE) {
-            if (L.last0) ux0 = -p[s].px[0];
-            if (L.last1) ux1 = -p[s].px[1];
-        }
-        un[s][0] = ((p[s].py[0] - h[s].py[0]) + ux0) - p[s].g[0];
-        un[s][1] = ((p[s].py[1] - h[s].py[1]) + ux1) - p[s].g[1];
-    }
-#pragma unroll
-    for (int s = 0; s < G; ++s) {
-        const double ur = shfl_down_d(h[s].u[0], 1);
-        upx[s][0] = h[s].u[1] - h[s].u[0]; upx[s][1] = ur - h[s].u[1];
-        if (EDGE) {
-            if (L.last0) upx[s][0] = 0.0;
-            if (L.last1) upx[s][1] = 0.0;
-        }
-    }
-#define CM_ALL for (int s = 0; s < G; ++s) for (int v = 0; v < 2; ++v)
-#pragma unroll
-    CM_ALL upy[s][v] = un[s][v] - h[s].u[v];
-#pragma unroll
-    CM_ALL s2[s][v] = fma(upx[s][v], upx[s][v], upy[s][v] * upy[s][v]);
-#pragma unroll
-    CM_ALL { const double y = fast_rsqrt_seed(s2[s][v] + 1e-300); gg[s][v] = s2[s][v] * y; hh[s][v] = 0.5 * y; }
-#pragma unroll
-    CM_ALL rs[s][v] = fast_rcp_seed(fma(tau, gg[s][v], 1.0));
-#pragma unroll
-    CM_ALL rr[s][v] = fma(-gg[s][v], hh[s][v], 0.5);
-#pragma unroll
-    CM_ALL { gg[s][v] = fma(gg[s][v], rr[s][v], gg[s][v]); hh[s][v] = fma(hh[s][v], rr[s][v], hh[s][v]); }
-#pragma unroll
-    CM_ALL rr[s][v] = fma(-gg[s][v], hh[s][v], 0.5);
-#pragma unroll
-    CM_ALL gg[s][v] = fma(gg[s][v], rr[s][v], gg[s][v]);                 // tmp = |grad u|   (:127)
-#pragma unroll
-    CM_ALL hh[s][v] = fma(tau, gg[s][v], 1.0);                           // d = 1 + tau*tmp
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-#pragma unroll
-        CM_ALL rr[s][v] = fma(-hh[s][v], rs[s][v], 1.0);
-#pragma unroll
-        CM_ALL rs[s][v] = fma(rs[s][v], rr[s][v], rs[s][v]);             // 1/d
-    }
-#pragma unroll
-    for (int s = 0; s < G; ++s) {
-        double e = 0.0;
-        CmPk o;
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const double ex = fma(gg[s][v], h[s].px[v], -upx[s][v]), ey = fma(gg[s][v], h[s].py[v], -upy[s][v]);
-            e += fma(ex, ex, ey * ey);                                   // :128
-            o.px[v] = fma(tau, upx[s][v], h[s].px[v]) * rs[s][v];        // :129
-            o.py[v] = fma(tau, upy[s][v], h[s].py[v]) * rs[s][v];        // :130
-            o.g[v] = h[s].g[v];
-        }
-        if (EDGE) {
-            if (!L.in0) { o.px[0] = 0.0; o.py[0] = 0.0; }
-            if (!L.in1) { o.px[1] = 0.0; o.py[1] = 0.0; }
-        }
-        err[s] += L.central ? e : 0.0;
-#pragma unroll
-        for (int v = 0; v < 2; ++v) { h[s].px[v] = p[s].px[v]; h[s].py[v] = p[s].py[v]; h[s].u[v] = un[s][v]; h[s].g[v] = p[s].g[v]; }
-        p[s] = o;
-    }
-#undef CM_ALL
-}
-
 // ZERO: the incoming dual pair is identically zero (chambolle_prox_TV_stop.m:68-69) and is not loaded
 template <bool EDGE, bool ZERO>
 __device__ __forceinline__ void cm_load(CmPk& p, const double* __restrict__ g, const double* __restrict__ px,
@@ -224,7 +147,8 @@ __device__ __forceinline__ void cm_store(const CmPk& p, double* __restrict__ pxo
 // chain).  PIPE = true: the levels are software-pipelined - level s consumes the
 // row level s-1 emitted in the PREVIOUS iteration (row r - 2s), the levels run
 // top-down and the T level steps of one iteration are independent (more ILP,
-// more registers).  inbox[s] is the row waiting for level s.
+// more registers; measured slower on B200 because ptxas keeps the level steps sequential anyway and
+// occupancy drops - only PIPE = false is instantiated).  inbox[s] is the row waiting for level s.
 __device__ __forceinline__ void cm_take(CmPk& dst, const CmPk& raw, double invlam) {
     dst.px[0] = raw.px[0]; dst.px[1] = raw.px[1]; dst.py[0] = raw.py[0]; dst.py[1] = raw.py[1];
     dst.g[0] = raw.g[0] * invlam; dst.g[1] = raw.g[1] * invlam;           // g / lambda (:124)
@@ -312,26 +236,13 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
         auto fast_body = [&](const CmPk& cur, int rr) {
             CmPk loc[T];
             cm_take(CM_BOX(0), cur, invlam);
-            if constexpr (PIPE) {
-                // all T levels are independent within the iteration: run them in lockstep groups
-                constexpr int G = (T % 2 == 0) ? 2 : T;
-                CmPk pk[T];
 #pragma unroll
-                for (int s = 0; s < T; ++s) pk[s] = inbox[s];
-#pragma unroll
-                for (int s0 = 0; s0 < T; s0 += G) cm_step_group<EDGE, G>(&h[s0], &pk[s0], L, tau, &err[s0]);
-                cm_store<EDGE>(pk[T - 1], pxo, pyo, (size_t)((long long)(rr - D * (T - 1) - 1) * nx + ibase), L);
-#pragma unroll
-                for (int s = 0; s + 1 < T; ++s) inbox[s + 1] = pk[s];
-            } else {
-#pragma unroll
-                for (int q = 0; q < T; ++q) {
-                    const int s = q;
-                    CmPk p = CM_BOX(s);
-                    cm_step<EDGE, false>(h[s], p, L, tau, err[s], false, false, true);
-                    if (s == T - 1) cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)(rr - D * (T - 1) - 1) * nx + ibase), L);
-                    else CM_BOX(s + 1) = p;
-                }
+            for (int q = 0; q < T; ++q) {
+                const int s = PIPE ? T - 1 - q : q;
+                CmPk p = CM_BOX(s);
+                cm_step<EDGE, false>(h[s], p, L, tau, err[s], false, false, true);
+                if (s == T - 1) cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)(rr - D * (T - 1) - 1) * nx + ibase), L);
+                else CM_BOX(s + 1) = p;
             }
         };
         if (r <= fast_hi) {
