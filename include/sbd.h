@@ -130,6 +130,20 @@ int sbd_likelihood(sbd_ctx* ctx, const double* x, const double* y, const double 
                    double sigma2, double theta, double scal[6], double* gradF);
 
 /* ------------------------------------------------------------------------
+ * Setup stage of the demo scripts, on the device.
+ *  sbd_max_eigenval : utils/max_eigenval_Gaussian_Moffat.m:1-27 / max_eigenval_Laplace.m:28-55 -
+ *                     power iteration on A'A at `psi`; x0 (rows x cols, nullable) is the start
+ *                     vector the reference draws with randn(im_size) (NULL -> Philox(seed)).
+ *  sbd_observe      : run_Gaussian_demo.m:145-168 - Ax = A(x; psi), sigma = ||Ax - mean(Ax)||_F /
+ *                     sqrt(numel * 10^(BSNR/10)), y = Ax + sigma * noise (noise nullable -> Philox).
+ *                     ax_norm (nullable) receives ||Ax - mean(Ax)||_F (for sigma_min / sigma_max).
+ * ---------------------------------------------------------------------- */
+int sbd_max_eigenval(sbd_ctx* ctx, const double psi[2], const double* x0, double tol, int max_iter,
+                     uint64_t seed, double* val, int* iters);
+int sbd_observe(sbd_ctx* ctx, const double* x, const double psi[2], double bsnr, const double* noise,
+                uint64_t seed, double* y, double* sigma, double* ax_norm);
+
+/* ------------------------------------------------------------------------
  * SAPG driver: SAPG/SAPG_algorithm_Guassian.m:7-308, SAPG_algorithm_moffat.m:7-297,
  * SAPG_algorithm_laplace.m:7-268 (warm-up MYULA + SAPG main loop + traces).
  * ---------------------------------------------------------------------- */

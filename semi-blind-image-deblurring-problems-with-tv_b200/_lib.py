@@ -80,6 +80,10 @@ SIGNATURES = {
                                  C.c_void_p, c_int_p, c_double_p, C.c_int]),
     "sbd_likelihood": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double,
                                  c_double_p, c_double_p]),
+    "sbd_max_eigenval": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_double, C.c_int, C.c_uint64,
+                                   c_double_p, c_int_p]),
+    "sbd_observe": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_uint64,
+                              c_double_p, c_double_p, c_double_p]),
     "sbd_sapg_run": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.POINTER(sbd_params),
                                c_double_p, C.POINTER(sbd_traces)]),
     "sbd_sapg_run_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(sbd_params), C.POINTER(sbd_traces)]),

@@ -216,6 +216,56 @@ __global__ void k_chain_mean(const double* __restrict__ in, double* __restrict__
     out[i] = s / (double)n;
 }
 
+// sum of x over one image -> out[0]   (mean(mean(Ax)), run_Gaussian_demo.m:148)
+__global__ void k_sum(const double* __restrict__ x, size_t npix, double* __restrict__ partials,
+                      unsigned int* __restrict__ counter, double* __restrict__ out) {
+    __shared__ double sm[32];
+    double acc[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) acc[0] += x[i];
+    block_sum<1>(acc, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
+    if (last_block_ticket(counter, gridDim.x)) {
+        if (threadIdx.x < 32) {
+            const double tot = warp_sum_partials(partials, (int)gridDim.x, 1);
+            if (threadIdx.x == 0) out[0] = tot;
+        }
+    }
+}
+
+__global__ void k_fill(double* __restrict__ x, size_t n, double v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
+__global__ void k_scale(double* __restrict__ x, size_t n, double a) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = x[i] * a;         // the reference divides (x = x/val); a = 1/val is passed as such
+}
+
+__global__ void k_div(double* __restrict__ x, size_t n, double d) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = x[i] / d;
+}
+
+// y = ax + sigma * z, z from `noise` or Philox (stream = 0xFFFF0000 + which)
+__global__ void k_add_noise(const double* __restrict__ ax, const double* __restrict__ noise, double sigma,
+                            double* __restrict__ y, size_t npix, uint64_t seed, uint32_t stream) {
+    const size_t pair = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * pair >= npix) return;
+    double2 z;
+    if (noise) z = *reinterpret_cast<const double2*>(noise + 2 * pair);
+    else z = philox_normal2(seed, stream, 0u, pair);
+    const double2 a = *reinterpret_cast<const double2*>(ax + 2 * pair);
+    *reinterpret_cast<double2*>(y + 2 * pair) = make_double2(a.x + sigma * z.x, a.y + sigma * z.y);
+}
+
+__global__ void k_philox_image(double* __restrict__ x, size_t npix, uint64_t seed, uint32_t stream) {
+    const size_t pair = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * pair >= npix) return;
+    const double2 z = philox_normal2(seed, stream, 0u, pair);
+    *reinterpret_cast<double2*>(x + 2 * pair) = z;
+}
+
 __global__ void k_bcast_image(const double* __restrict__ src, double* __restrict__ dst, size_t npix, int n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;

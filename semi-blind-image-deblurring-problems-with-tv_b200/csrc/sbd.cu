@@ -788,6 +788,85 @@ int sbd_likelihood(sbd_ctx* c, const double* x, const double* y, const double ps
     SBD_CATCH(c)
 }
 
+// ---------------------------------------------------------------- setup stage
+static double image_sumsq_vs(sbd_ctx* c, const double* d_x, const double* d_ref) {
+    k_sqdiff<<<dim3(256, 1), 256, 0, c->stream>>>(d_x, d_ref, c->npix, c->part_sq, c->cnt_sq, c->stats);
+    LAUNCH_CHECK(c);
+    double st[NSTAT];
+    SBD_CUDA(cudaMemcpyAsync(st, c->stats, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    return st[4];
+}
+
+int sbd_max_eigenval(sbd_ctx* c, const double psi[2], const double* x0, double tol, int max_iter,
+                     uint64_t seed, double* val, int* iters) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(psi && val && max_iter >= 1, SBD_E_INVALID, "sbd_max_eigenval: bad argument");
+    require_pow2(c);
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, 1);
+    const size_t n = c->npix, bytes = sizeof(double) * n;
+    const unsigned gb = (unsigned)((n + 255) / 256), gp = (unsigned)((n / 2 + 255) / 256);
+    double* zero = c->ximg;                                         // all-zero image for the norms
+    SBD_CUDA(cudaMemsetAsync(zero, 0, bytes, c->stream));
+    if (x0) SBD_CUDA(cudaMemcpyAsync(c->X, x0, bytes, cudaMemcpyHostToDevice, c->stream));
+    else { k_philox_image<<<gp, 256, 0, c->stream>>>(c->X, n, seed, 0xFFFF0001u); LAUNCH_CHECK(c); }
+    double nrm = std::sqrt(image_sumsq_vs(c, c->X, zero));
+    k_div<<<gb, 256, 0, c->stream>>>(c->X, n, nrm); LAUNCH_CHECK(c);    // x = x/norm(x(:))          :5
+    psf_from_host(c, psi, c->nk);
+    double init_val = 1.0, v = 0.0;                                     // :6
+    int k = 0;
+    for (k = 1; k <= max_iter; ++k) {                                   // :8
+        rows_fwd(c, c->X, c->S1, 1); cols<COL_OP>(c, c->S1, c->S1, 1, SBD_OP_A); rows_inv(c, c->S1, c->P, 1);    // y = A(x)   :9
+        rows_fwd(c, c->P, c->S1, 1); cols<COL_OP>(c, c->S1, c->S1, 1, SBD_OP_AT); rows_inv(c, c->S1, c->X, 1);   // x = At(y)  :10
+        v = std::sqrt(image_sumsq_vs(c, c->X, zero));                   // val = norm(x(:))           :11
+        const double rel_var = std::fabs(v - init_val) / init_val;      // :12
+        if (rel_var < tol) break;                                       // :16-18
+        init_val = v;                                                   // :19
+        k_div<<<gb, 256, 0, c->stream>>>(c->X, n, v); LAUNCH_CHECK(c);  // x = x/val                  :20
+    }
+    *val = v;
+    if (iters) *iters = std::min(k, max_iter);
+    SBD_CATCH(c)
+}
+
+int sbd_observe(sbd_ctx* c, const double* x, const double psi[2], double bsnr, const double* noise,
+                uint64_t seed, double* y, double* sigma, double* ax_norm) {
+    if (!c) return SBD_E_INVALID;
+    SBD_TRY(c)
+    SBD_REQUIRE(x && psi && y, SBD_E_INVALID, "sbd_observe: bad argument");
+    require_pow2(c);
+    SBD_CUDA(cudaSetDevice(c->device));
+    ensure_ws(c, 1);
+    const size_t n = c->npix, bytes = sizeof(double) * n;
+    const unsigned gb = (unsigned)((n + 255) / 256), gp = (unsigned)((n / 2 + 255) / 256);
+    SBD_CUDA(cudaMemcpyAsync(c->X, x, bytes, cudaMemcpyHostToDevice, c->stream));
+    psf_from_host(c, psi, c->nk);
+    rows_fwd(c, c->X, c->S1, 1); cols<COL_OP>(c, c->S1, c->S1, 1, SBD_OP_A); rows_inv(c, c->S1, c->P, 1);        // Ax  :145
+    k_sum<<<256, 256, 0, c->stream>>>(c->P, n, c->part_sq, c->cnt_sq, c->stats + 5);
+    LAUNCH_CHECK(c);
+    double st[NSTAT];
+    SBD_CUDA(cudaMemcpyAsync(st, c->stats, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    const double mean = st[5] / (double)n;                              // mean(mean(Ax))             :148
+    k_fill<<<gb, 256, 0, c->stream>>>(c->ximg, n, mean); LAUNCH_CHECK(c);
+    const double nrm = std::sqrt(image_sumsq_vs(c, c->P, c->ximg));     // norm(Ax-mean,'fro')
+    const double sg = nrm / std::sqrt((double)n * std::pow(10.0, bsnr / 10.0));      // :148
+    double* d_noise = nullptr;
+    if (noise) {
+        d_noise = c->Gf;
+        SBD_CUDA(cudaMemcpyAsync(d_noise, noise, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    k_add_noise<<<gp, 256, 0, c->stream>>>(c->P, d_noise, sg, c->X, n, seed, 0xFFFF0002u);   // y = Ax + sigma*noise  :166-168
+    LAUNCH_CHECK(c);
+    SBD_CUDA(cudaMemcpyAsync(y, c->X, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SBD_CUDA(cudaStreamSynchronize(c->stream));
+    if (sigma) *sigma = sg;
+    if (ax_norm) *ax_norm = nrm;
+    SBD_CATCH(c)
+}
+
 // ---------------------------------------------------------------- comm
 int sbd_comm_unique_id(char id[SBD_NCCL_ID_BYTES]) {
     if (!id) return SBD_E_INVALID;

@@ -156,6 +156,24 @@ class Engine:
             out["gradF"] = self._unimg(gf, 1, True)
         return out
 
+    # -- setup stage of the demos ---------------------------------------------
+    def max_eigenval(self, psi, tol=1e-4, max_iter=10000, x0=None, seed=1):
+        """utils/max_eigenval_Gaussian_Moffat.m / max_eigenval_Laplace.m -> (val, iterations)."""
+        x0b = self._img(x0, "x0")[0] if x0 is not None else None
+        val = C.c_double(); it = C.c_int()
+        self._check(lib.sbd_max_eigenval(self._h, _p(_psi(psi)), _p(x0b), float(tol), int(max_iter), int(seed),
+                                         C.byref(val), C.byref(it)))
+        return val.value, it.value
+
+    def observe(self, x, psi, bsnr, noise=None, seed=1):
+        """run_Gaussian_demo.m:145-168 -> (y, sigma, ||Ax - mean(Ax)||_F)."""
+        xb, _ = self._img(x)
+        nb = self._img(noise, "noise")[0] if noise is not None else None
+        y = np.empty_like(xb); sg = C.c_double(); nr = C.c_double()
+        self._check(lib.sbd_observe(self._h, _p(xb), _p(_psi(psi)), float(bsnr), _p(nb), int(seed), _p(y),
+                                    C.byref(sg), C.byref(nr)))
+        return self._unimg(y, 1, True), sg.value, nr.value
+
     # -- SAPG -----------------------------------------------------------------
     def sapg(self, y, prm, X0=None, x_true=None, noise=None, want_X_warm=True, want_X_mean=False):
         """Run sbd_sapg_run.  `prm` is a filled sbd_params; noise (optional)

@@ -138,3 +138,25 @@ def test_sapg_vs_reference_execution(sbd, name):
             assert rel(got[m], want[m]) < TRAJ_TOL, (f, rel(got[m], want[m]))
         checked += 1
     assert checked >= 25
+
+
+@pytest.mark.parametrize("name", ["gaussian", "moffat", "laplace"])
+def test_setup_stage_vs_reference_execution(sbd, name):
+    """max_eigenval_* power iteration and the observation synthesis of the demo scripts, on the
+    device, against the values the reference execution produced (evMax, sigma, y)."""
+    g = dict(np.load(os.path.join(GOLDEN, f"ref_sapg_{name}.npz")))
+    rng = np.random.default_rng(int(sc(g["seed"])))
+    shape = g["x"].shape
+    x0 = rng.standard_normal(shape)                 # the power iteration's randn(im_size)   (Q21)
+    noise = rng.standard_normal(shape)              # the observation noise
+    eng = sbd.engine_for(shape, 7, MODELS[name], 0.0)
+    ev_psi = {"gaussian": (1.0, 1.0), "moffat": (1.0, 5.0), "laplace": (1.0,)}[name]     # demo scripts :142/:140/:110
+    true_psi = {"gaussian": (0.4, 0.3), "moffat": (0.4, 3.5), "laplace": (0.3,)}[name]
+    val, iters = eng.max_eigenval(ev_psi, 1e-4, 10000, x0=x0)
+    assert abs(val - sc(g["evMax"])) <= 1e-11 * sc(g["evMax"]) and iters > 1
+    y, sigma, nrm = eng.observe(g["x"], true_psi, 30, noise=noise)
+    assert abs(sigma - sc(g["op_sigma"])) <= 1e-12 * sc(g["op_sigma"])
+    assert rel(y, g["y"]) < TOL
+    # Philox start vector: converges to the same eigenvalue within the stop tolerance
+    val2, _ = eng.max_eigenval(ev_psi, 1e-4, 10000, seed=3)
+    assert abs(val2 - val) < 3e-2 * val      # the 1e-4 stop rule leaves a start-vector dependence of ~1%
