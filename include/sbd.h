@@ -144,6 +144,19 @@ int sbd_observe(sbd_ctx* ctx, const double* x, const double psi[2], double bsnr,
                 uint64_t seed, double* y, double* sigma, double* ax_norm);
 
 /* ------------------------------------------------------------------------
+ * Post-SAPG MAP estimate: SALSA/SALSA_v2.m:156-494 as the demos configure it
+ * (run_Gaussian_demo.m:210-242): ADMM with the TV prox computed by chambolle_prox_TV_stop
+ * warm-started from the previous dual pair ('TVINITIALIZATION',1,'TViters',tv_iters), the
+ * least-squares step invLS = real(ifft2(fft2(.) ./ (|H|^2 + mu))), zero initialisation,
+ * stopping criterion 1 (relative change of the objective < tolA, at most maxiter iterations).
+ *   objective [maxiter+1], distance [maxiter], mses [maxiter+1] (nullable; mses needs x_true).
+ *   n_outer receives the number of outer iterations executed.
+ * ---------------------------------------------------------------------- */
+int sbd_salsa_tv(sbd_ctx* ctx, const double* y, const double psi[2], double tau, double mu, int maxiter,
+                 double tolA, int tv_iters, const double* x_true, double* x, double* objective,
+                 double* distance, double* mses, int* n_outer);
+
+/* ------------------------------------------------------------------------
  * SAPG driver: SAPG/SAPG_algorithm_Guassian.m:7-308, SAPG_algorithm_moffat.m:7-297,
  * SAPG_algorithm_laplace.m:7-268 (warm-up MYULA + SAPG main loop + traces).
  * ---------------------------------------------------------------------- */

@@ -25,7 +25,7 @@ import numpy as np
 # tokenizer
 # ---------------------------------------------------------------------------
 KEYWORDS = {"function", "if", "elseif", "else", "end", "for", "while", "switch", "case", "otherwise",
-            "break", "return", "global", "continue"}
+            "break", "return", "global", "continue", "try", "catch"}
 TOKEN_RE = re.compile(r"""
     (?P<num>(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?) |
     (?P<id>[A-Za-z_]\w*) |
@@ -241,6 +241,17 @@ class Parser:
             if tk.val in ("break", "return", "continue"):
                 self.next()
                 return (tk.val,)
+            if tk.val == "try":
+                self.next()
+                body = self.parse_block(("catch", "end"))
+                handler = []
+                if self.at("catch"):
+                    self.next()
+                    if self.peek().kind == "id" and self.peek(1).kind == "nl":
+                        self.next()                 # catch ME
+                    handler = self.parse_block(("end",))
+                self.expect("end")
+                return ("try", body, handler)
             if tk.val == "global":
                 self.next()
                 names = []
@@ -736,6 +747,11 @@ class Interp:
                     return
             if st[3] is not None:
                 self.exec_block(st[3], scope, local)
+        elif k == "try":
+            try:
+                self.exec_block(st[1], scope, local)
+            except MatlabError:
+                self.exec_block(st[2], scope, local)
         elif k == "break":
             raise BreakEx()
         elif k == "continue":
@@ -744,7 +760,8 @@ class Interp:
             raise ReturnEx()
         elif k == "global":
             for n in st[1]:
-                scope[n] = self.globals.setdefault(n, M(0.0))
+                scope[n] = self.globals.setdefault(n, np.zeros((0, 0)))
+                scope.setdefault("__globals__", set()).add(n)
         else:
             raise MatlabError(f"unknown statement {k}")
 
@@ -753,6 +770,8 @@ class Interp:
         k = tgt[0]
         if k == "id":
             scope[tgt[1]] = val
+            if tgt[1] in scope.get("__globals__", ()):
+                self.globals[tgt[1]] = val
         elif k == "field":
             base = self._lvalue_struct(tgt[1], scope, local)
             base[tgt[2]] = val
@@ -929,6 +948,8 @@ class Interp:
         if k == "id":
             name = e[1]
             if name in scope:
+                if name in scope.get("__globals__", ()):
+                    return [self.globals[name]]
                 return [scope[name]]
             return self.call_function(name, [], nargout, local)
         if k == "field":
@@ -1084,6 +1105,11 @@ class Interp:
             base = scope[target[1]]
         elif target[0] == "id":
             args = [self.eval(a, scope, local, end_val) for a in arg_exprs]
+            if target[1] == "exist":                # exist('name','var') looks at the caller's workspace
+                name = args[0]
+                if len(args) > 1 and args[1] == "var":
+                    return [M(float(name in scope))]
+                return [M(1.0 if name in scope else (2.0 if self._find(name) is not None or name in self.builtins else 0.0))]
             return self.call_function(target[1], args, nargout, local)
         else:
             base = self.eval(target, scope, local, end_val)
@@ -1268,6 +1294,24 @@ class Interp:
             raise MatlabError(a[0] if a else "error")
         B["error"] = error_
         B["isreal"] = lambda a, n: [M(float(not np.iscomplexobj(M(a[0]))))]
+
+        def isa_(a, n):
+            kind = a[1]
+            v = a[0]
+            if kind == "function_handle":
+                return [M(float(isinstance(v, MFunc)))]
+            if kind in ("double", "numeric", "float"):
+                return [M(float(is_num(v)))]
+            if kind == "struct":
+                return [M(float(isinstance(v, MStruct)))]
+            if kind == "char":
+                return [M(float(isinstance(v, str)))]
+            return [M(0.0)]
+        B["isa"] = isa_
+        B["xor"] = lambda a, n: [M(float(truth(a[0]) != truth(a[1])))]
+        B["rem"] = lambda a, n: [np.fmod(M(a[0]), M(a[1]))]
+        B["transpose"] = lambda a, n: [M(a[0]).T.copy()]
+        B["inv"] = lambda a, n: [np.linalg.inv(M(a[0]))]
         B["any"] = lambda a, n: [M(float(np.any(M(a[0]) != 0)))]
         B["all"] = lambda a, n: [M(float(np.all(M(a[0]) != 0)))]
         B["svd"] = lambda a, n: [np.linalg.svd(M(a[0]), compute_uv=False).reshape(-1, 1)]

@@ -84,6 +84,8 @@ SIGNATURES = {
                                    c_double_p, c_int_p]),
     "sbd_observe": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_uint64,
                               c_double_p, c_double_p, c_double_p]),
+    "sbd_salsa_tv": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int,
+                               c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
     "sbd_sapg_run": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.POINTER(sbd_params),
                                c_double_p, C.POINTER(sbd_traces)]),
     "sbd_sapg_run_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(sbd_params), C.POINTER(sbd_traces)]),

@@ -312,7 +312,8 @@ enum ColMode {
     COL_FWD = 0,            // spectrum of y (no PSF work)
     COL_FWD_REDUCE = 1,     // X^ = fft; store; rss, c0, c1 against Y^ with the CURRENT parameters
     COL_MUL_INV = 2,        // G^ = conj(H)(H X^ - Y^) * inv_scale ; inverse fft ; store
-    COL_OP = 3              // fft ; multiply by the selected kernel / (nx*ny) ; inverse fft ; store
+    COL_OP = 3,             // fft ; multiply by the selected kernel / (nx*ny) ; inverse fft ; store
+    COL_FILTER = 4          // fft ; X^ = R^ / (|H|^2 + mu) ; rss = sum |Y^ - H X^|^2 ; inverse fft ; store   (SALSA invLS)
 };
 
 struct ColArgs {
@@ -329,6 +330,7 @@ struct ColArgs {
     int nk, nxfull, t, npsi, C, logC, opsel;   // C = columns per block
     int LC, nsub, ntiles;                      // layout tile width, blocks per tile, tiles per image
     double opscale;
+    double mu;              // COL_FILTER: the ADMM penalty in 1/(|H|^2 + mu)   (run_Gaussian_demo.m:224)
 };
 
 template <int N, int MODE>
@@ -395,9 +397,23 @@ __global__ void k_cols(const ColArgs a) {
         }
     };
 
-    if (MODE == COL_OP) {
+    if (MODE == COL_OP || MODE == COL_FILTER) {
         // forward transform ending in shared memory, multiply, inverse transform from shared memory
         auto sdst = [&](int q, double2 v) {
+            if (MODE == COL_FILTER) {
+                const double2 w = __ldg(a.tw + q);
+                const double2 H = psf_horner(coefS[c][0], a.t, w);
+                const double F = 1.0 / ((H.x * H.x + H.y * H.y) + a.mu);       // filter_FFT, demo:224
+                const double2 X = make_double2(v.x * F, v.y * F);
+                if (kin) {
+                    const double2 yv = __ldg(yh + (size_t)q * LC + c);
+                    const double2 R = csub(yv, cmul(H, X));                       // Y^ - H X^
+                    const double wt = (k == 0 || 2 * k == a.nxfull) ? 1.0 : 2.0;
+                    acc[0] += wt * (R.x * R.x + R.y * R.y);
+                }
+                line[fft_pad<N>(q) * C] = make_double2(X.x * a.opscale, X.y * a.opscale);
+                return;
+            }
             const double2 w = __ldg(a.tw + q);
             const int m = (a.opsel == SBD_OP_A || a.opsel == SBD_OP_AT) ? 0 : (a.opsel == SBD_OP_D0 ? 1 : 2);
             double2 K = psf_horner(coefS[c][m], a.t, w);
@@ -454,7 +470,7 @@ __global__ void k_cols(const ColArgs a) {
         fft_run<N, false, false>(active, tl, line, C, a.tw, gsrc, gdst);
     }
 
-    if (MODE == COL_FWD_REDUCE) {
+    if (MODE == COL_FWD_REDUCE || MODE == COL_FILTER) {
         block_sum<3>(acc, redS);
         const unsigned int ntiles = gridDim.x;
         double* part = a.partials + (size_t)img * ntiles * 4;

@@ -266,6 +266,48 @@ __global__ void k_philox_image(double* __restrict__ x, size_t npix, uint64_t see
     *reinterpret_cast<double2*>(x + 2 * pair) = z;
 }
 
+// ---- SALSA (ADMM) elementwise pieces, SALSA/SALSA_v2.m:428-450 ----------------------------
+// v = PTx - bu                                                                (:428 argument)
+__global__ void k_salsa_pre(const double* __restrict__ x, const double* __restrict__ bu, double* __restrict__ v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = x[i] - bu[i];
+}
+// r = ATy + mu*(u + bu)                                                       (:433)
+__global__ void k_salsa_r(const double* __restrict__ aty, const double* __restrict__ u, const double* __restrict__ bu,
+                          double mu, double* __restrict__ r, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) r[i] = aty[i] + mu * (u[i] + bu[i]);
+}
+// bu = bu + (u - x) (:439) and the sums for `distance` (:450) and `mses` (:447):
+// out[0] = sum (x-u)^2, out[1] = sum x^2, out[2] = sum u^2, out[3] = sum (x-true)^2
+__global__ void k_salsa_post(const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ bu,
+                             const double* __restrict__ xtrue, size_t n, double* __restrict__ partials,
+                             unsigned int* __restrict__ counter, double* __restrict__ out) {
+    __shared__ double sm[4 * 32];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double xv = x[i], uv = u[i];
+        bu[i] = bu[i] + (uv - xv);
+        const double d = xv - uv;
+        acc[0] += d * d; acc[1] += xv * xv; acc[2] += uv * uv;
+        if (xtrue) { const double e = xv - xtrue[i]; acc[3] += e * e; }
+    }
+    block_sum<4>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) partials[q * gridDim.x + blockIdx.x] = acc[q];
+    }
+    if (last_block_ticket(counter, gridDim.x)) {
+        if (threadIdx.x < 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double tot = warp_sum_partials(partials + q * gridDim.x, (int)gridDim.x, 1);
+                if (threadIdx.x == 0) out[q] = tot;
+            }
+        }
+    }
+}
+
 __global__ void k_bcast_image(const double* __restrict__ src, double* __restrict__ dst, size_t npix, int n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;

@@ -75,6 +75,7 @@ struct sbd_ctx {
     int tvV = 1, tv_gx = 1, tv_gy = 1, tv_seg = 8, tv_parts = 1;
     int cmT = 5, cm_strips = 1, cm_gx = 1, cm_gy = 1, cm_seg = 128;     // fused Chambolle geometry
     bool cm_pipe = false;
+    double salsa_mu = 0.0;
     int cm_minb = 3;
     int rowsLP = 1, rowsT = 32, colsC = 2, colsLogC = 1, colsT = 32, ntiles = 1;
     int colsKC = 2, colsLogKC = 1;     // columns per block of the column pass (<= colsC, the layout tile width)
@@ -405,6 +406,7 @@ void cols(sbd_ctx* c, const double2* in, double2* out, int batch, int opsel = 0)
     a.npsi = (c->model == SBD_LAPLACE) ? 1 : 2; a.C = c->colsKC; a.logC = c->colsLogKC; a.LC = c->colsC;
     a.nsub = c->colsC / c->colsKC; a.ntiles = c->ntiles; a.opsel = opsel;
     a.opscale = 1.0 / ((double)c->nx * (double)c->ny);
+    a.mu = c->salsa_mu;
     const size_t smem = c->cols_smem;
     dim3 g(c->ntiles * (c->colsC / c->colsKC), batch);
     switch (c->ny) {
@@ -865,6 +867,85 @@ int sbd_observe(sbd_ctx* c, const double* x, const double psi[2], double bsnr, c
     if (sigma) *sigma = sg;
     if (ax_norm) *ax_norm = nrm;
     SBD_CATCH(c)
+}
+
+// ---------------------------------------------------------------- SALSA MAP (post-SAPG)
+int sbd_salsa_tv(sbd_ctx* c, const double* y, const double psi[2], double tau, double mu, int maxiter,
+                 double tolA, int tv_iters, const double* x_true, double* x, double* objective,
+                 double* distance, double* mses, int* n_outer) {
+    if (!c) return SBD_E_INVALID;
+    double *d_aty = nullptr, *d_u = nullptr, *d_bu = nullptr, *d_xt = nullptr;
+    int rc = SBD_OK;
+    try {
+        SBD_REQUIRE(y && psi && x && maxiter >= 1 && tv_iters >= 1 && mu > 0.0, SBD_E_INVALID, "sbd_salsa_tv: bad argument");
+        require_pow2(c);
+        SBD_CUDA(cudaSetDevice(c->device));
+        ensure_ws(c, 1);
+        cudaStream_t s = c->stream;
+        const size_t n = c->npix, bytes = sizeof(double) * n;
+        const unsigned gb = (unsigned)((n + 255) / 256);
+        const double P = (double)n;
+        d_aty = dalloc<double>(n); d_u = dalloc<double>(n); d_bu = dalloc<double>(n);
+        if (x_true) { d_xt = dalloc<double>(n); SBD_CUDA(cudaMemcpyAsync(d_xt, x_true, bytes, cudaMemcpyHostToDevice, s)); }
+        // Y^, ATy = AT(y)                                                        SALSA_v2.m:287
+        SBD_CUDA(cudaMemcpyAsync(c->ximg, y, bytes, cudaMemcpyHostToDevice, s));
+        psf_from_host(c, psi, c->nk);
+        rows_fwd(c, c->ximg, c->yhat, 1);
+        cols<COL_FWD>(c, c->yhat, c->yhat, 1);
+        // COL_OP takes the rows-pass output (it does the forward column transform itself)
+        rows_fwd(c, c->ximg, c->S1, 1);
+        cols<COL_OP>(c, c->S1, c->S1, 1, SBD_OP_AT);
+        rows_inv(c, c->S1, d_aty, 1);
+        // x = AT(0) = 0, u = x, bu = 0, pux = puy = 0                            :368, :391-392, :418-419
+        double* d_x = c->X;
+        SBD_CUDA(cudaMemsetAsync(d_x, 0, bytes, s));
+        SBD_CUDA(cudaMemsetAsync(d_u, 0, bytes, s));
+        SBD_CUDA(cudaMemsetAsync(d_bu, 0, bytes, s));
+        SBD_CUDA(cudaMemsetAsync(c->px0, 0, bytes, s));
+        SBD_CUDA(cudaMemsetAsync(c->py0, 0, bytes, s));
+        // prev_f = 0.5*||y - A(0)||^2 + tau*phi(0) ; mses(1)                      :398-400, :414
+        SBD_CUDA(cudaMemsetAsync(c->Gf, 0, bytes, s));
+        double st[NSTAT];
+        const double yy = image_sumsq_vs(c, c->ximg, c->Gf);
+        double prev_obj = 0.5 * yy;
+        if (objective) objective[0] = prev_obj;
+        if (mses && x_true) mses[0] = image_sumsq_vs(c, d_xt, c->Gf) / P;
+        const double threshold = tau / mu;                                        // :393
+        set_chamb_options(c, threshold, tv_iters, 1e-3, 0.249);
+        c->salsa_mu = mu;
+        int outer = 0;
+        for (outer = 1; outer <= maxiter; ++outer) {                              // :422
+            k_salsa_pre<<<gb, 256, 0, s>>>(d_x, d_bu, c->P, n); LAUNCH_CHECK(c);                 // PTx - bu
+            chambolle(c, c->P, d_u, 1, tv_iters, false);                          // :428 (warm start from px0/py0)
+            k_salsa_r<<<gb, 256, 0, s>>>(d_aty, d_u, d_bu, mu, c->Gf, n); LAUNCH_CHECK(c);       // :433
+            rows_fwd(c, c->Gf, c->S1, 1);
+            cols<COL_FILTER>(c, c->S1, c->S1, 1);                                 // x = invLS(r), rss = ||y - A x||^2   :435, :441
+            rows_inv(c, c->S1, d_x, 1);
+            k_salsa_post<<<256, 256, 0, s>>>(d_x, d_u, d_bu, d_xt, n, c->part_sq, c->cnt_sq, c->stats + 2);   // :439
+            LAUNCH_CHECK(c);
+            tvnorm(c, d_u, c->stats, NSTAT, 1);                                   // phi(u)
+            ChambState hs;
+            SBD_CUDA(cudaMemcpyAsync(st, c->stats, sizeof st, cudaMemcpyDeviceToHost, s));
+            SBD_CUDA(cudaMemcpyAsync(&hs, c->chst, sizeof hs, cudaMemcpyDeviceToHost, s));
+            SBD_CUDA(cudaStreamSynchronize(s));
+            if (hs.buf) { std::swap(c->px0, c->px1); std::swap(c->py0, c->py1); }  // next warm start reads px0/py0
+            const double obj = 0.5 * st[1] + tau * st[0];                         // :443  (st[1] = rss, Parseval)
+            if (objective) objective[outer] = obj;
+            if (mses && x_true) mses[outer] = st[5] / P;                          // :447
+            if (distance) distance[outer - 1] = std::sqrt(st[2]) / std::sqrt(st[3] + st[4]);      // :450
+            bool stop = false;
+            if (outer > 1) stop = std::fabs(obj - prev_obj) / prev_obj < tolA;    // :457, :470
+            prev_obj = obj;
+            if (stop) break;
+        }
+        if (n_outer) *n_outer = std::min(outer, maxiter);
+        SBD_CUDA(cudaMemcpyAsync(x, d_x, bytes, cudaMemcpyDeviceToHost, s));
+        SBD_CUDA(cudaStreamSynchronize(s));
+    } catch (const Error& e) {
+        rc = fail(c, e);
+    }
+    cudaFree(d_aty); cudaFree(d_u); cudaFree(d_bu); cudaFree(d_xt);
+    return rc;
 }
 
 // ---------------------------------------------------------------- comm

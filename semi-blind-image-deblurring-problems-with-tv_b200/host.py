@@ -174,6 +174,21 @@ class Engine:
                                     C.byref(sg), C.byref(nr)))
         return self._unimg(y, 1, True), sg.value, nr.value
 
+    # -- post-SAPG MAP estimate -----------------------------------------------
+    def salsa_tv(self, y, psi, tau, mu, maxiter=500, tolA=1e-5, tv_iters=10, x_true=None):
+        """SALSA_v2 as the demos call it (run_Gaussian_demo.m:229-242) ->
+        dict(x, objective, distance, mses, n_outer, numA, numAt)."""
+        yb, _ = self._img(y, "y")
+        xt = self._img(x_true, "x_true")[0] if x_true is not None else None
+        x = np.empty_like(yb)
+        obj = np.zeros(maxiter + 1); dist = np.zeros(maxiter); mses = np.zeros(maxiter + 1)
+        n = C.c_int()
+        self._check(lib.sbd_salsa_tv(self._h, _p(yb), _p(_psi(psi)), float(tau), float(mu), int(maxiter), float(tolA),
+                                     int(tv_iters), _p(xt), _p(x), _p(obj), _p(dist), _p(mses), C.byref(n)))
+        k = n.value
+        return dict(x=self._unimg(x, 1, True), objective=obj[:k + 1], distance=dist[:k],
+                    mses=mses[:k + 1] if x_true is not None else np.zeros(0), n_outer=k, numA=k + 1, numAt=1)
+
     # -- SAPG -----------------------------------------------------------------
     def sapg(self, y, prm, X0=None, x_true=None, noise=None, want_X_warm=True, want_X_mean=False):
         """Run sbd_sapg_run.  `prm` is a filled sbd_params; noise (optional)

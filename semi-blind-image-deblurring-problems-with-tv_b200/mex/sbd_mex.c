@@ -19,6 +19,10 @@
  *   out     = sbd_mex('blur', x, model, t, phi, psi, op)                  A / AT / dif_* closures
  *   s       = sbd_mex('likelihood', x, y, model, t, phi, psi, sigma2, theta)   op.f, op.gradF, op.grad_psi, ...
  *   r       = sbd_mex('sapg', y, X0, xtrue, model, t, phi, P, noise)      SAPG/SAPG_algorithm_*.m
+ *   [v,k]   = sbd_mex('max_eigenval', [M N], model, t, phi, psi, tol, maxit, x0)   utils/max_eigenval_*.m
+ *   [y,s,n] = sbd_mex('observe', x, model, t, phi, psi, bsnr, noise)      run_Gaussian_demo.m:145-168
+ *   [x,obj,dist,mses] = sbd_mex('salsa', y, model, t, phi, psi, tau, mu, maxiter, tolA, tviters, xtrue)
+ *                                                                         SALSA/SALSA_v2.m as the demos call it
  *
  * Build:  mex -I../../include sbd_mex.c -L../lib -lsbd          (MATLAB)
  *         mkoctfile --mex -I../../include sbd_mex.c -L../lib -lsbd   (Octave)
@@ -228,6 +232,48 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         mxSetField(r, 0, "seconds", mxCreateDoubleScalar(t.seconds));
         mxSetField(r, 0, "last_samp", mxCreateDoubleScalar((double)t.last_samp));
         plhs[0] = r;
+    } else if (!strcmp(cmd, "max_eigenval")) {
+        const double* sz = mxGetPr(prhs[1]);
+        double psi[2], val = 0.0;
+        int it = 0;
+        sbd_ctx* c;
+        const double* x0 = (nrhs > 8 && !mxIsEmpty(prhs[8])) ? mxGetPr(prhs[8]) : NULL;
+        rows = (int)sz[0]; cols = (int)sz[1];
+        c = get_ctx(rows, cols, (int)mxGetScalar(prhs[3]), (int)mxGetScalar(prhs[2]), mxGetScalar(prhs[4]), 1);
+        psi_of(prhs[5], psi);
+        rc = sbd_max_eigenval(c, psi, x0, mxGetScalar(prhs[6]), (int)mxGetScalar(prhs[7]), 1, &val, &it);
+        if (rc) fail(c, "sbd_max_eigenval", rc);
+        plhs[0] = mxCreateDoubleScalar(val);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar((double)it);
+    } else if (!strcmp(cmd, "observe")) {
+        const double* x = image(prhs[1], "x", &rows, &cols);
+        double psi[2], sg = 0.0, nr = 0.0;
+        const double* noise = (nrhs > 7 && !mxIsEmpty(prhs[7])) ? mxGetPr(prhs[7]) : NULL;
+        sbd_ctx* c = get_ctx(rows, cols, (int)mxGetScalar(prhs[3]), (int)mxGetScalar(prhs[2]), mxGetScalar(prhs[4]), 1);
+        psi_of(prhs[5], psi);
+        plhs[0] = mxCreateDoubleMatrix(rows, cols, mxREAL);
+        rc = sbd_observe(c, x, psi, mxGetScalar(prhs[6]), noise, 1, mxGetPr(plhs[0]), &sg, &nr);
+        if (rc) fail(c, "sbd_observe", rc);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(sg);
+        if (nlhs > 2) plhs[2] = mxCreateDoubleScalar(nr);
+    } else if (!strcmp(cmd, "salsa")) {
+        const double* y = image(prhs[1], "y", &rows, &cols);
+        double psi[2], *obj, *dist, *ms;
+        const int maxiter = (int)mxGetScalar(prhs[8]);
+        const double* xt = (nrhs > 11 && !mxIsEmpty(prhs[11])) ? mxGetPr(prhs[11]) : NULL;
+        int n = 0;
+        mxArray *o, *d, *m;
+        sbd_ctx* c = get_ctx(rows, cols, (int)mxGetScalar(prhs[3]), (int)mxGetScalar(prhs[2]), mxGetScalar(prhs[4]), 1);
+        psi_of(prhs[5], psi);
+        plhs[0] = mxCreateDoubleMatrix(rows, cols, mxREAL);
+        o = vec(maxiter + 1, &obj); d = vec(maxiter, &dist); m = vec(maxiter + 1, &ms);
+        rc = sbd_salsa_tv(c, y, psi, mxGetScalar(prhs[6]), mxGetScalar(prhs[7]), maxiter, mxGetScalar(prhs[9]),
+                          (int)mxGetScalar(prhs[10]), xt, mxGetPr(plhs[0]), obj, dist, ms, &n);
+        if (rc) fail(c, "sbd_salsa_tv", rc);
+        if (nlhs > 1) plhs[1] = o;
+        if (nlhs > 2) plhs[2] = d;
+        if (nlhs > 3) plhs[3] = m;
+        if (nlhs > 4) plhs[4] = mxCreateDoubleScalar((double)n);
     } else {
         mexErrMsgIdAndTxt("sbd:usage", "unknown command '%s'", cmd);
     }

@@ -170,7 +170,35 @@ def sapg(model, seed):
     print(f"ref_sapg_{model}.npz:", len(out), "arrays; last theta", np.ravel(out["res_thetas"])[-1])
 
 
+def salsa(seed=7):
+    """run_Gaussian_demo.m:210-244 verbatim (A1/AT1 with callcounter, mu, filter_FFT, invLS, the SALSA_v2 call
+    and the MSE line), fed with fixed estimates instead of a 35 000-iteration SAPG run."""
+    it = new_interp(seed)
+    x = crop("cman_u8.npy", 96, 64, 32, 32)
+    sc = {"x": x}
+    it.run_source(lines_of("run_Gaussian_demo.m", 34, 88), sc)
+    it.run_source("snr = 30; op.BSNR = snr; dimX = numel(x); op.x = x;\n", sc)
+    it.run_source(lines_of("run_Gaussian_demo.m", 123, 195), sc)
+    it.run_source("theta_EB = 0.045; w1_EB = 0.43; w2_EB = 0.28; sigma_EB = 4.2;\n", sc)
+    it.run_source(lines_of("run_Gaussian_demo.m", 210, 244), sc)
+    out = {"x": x, "y": sc["y"], "seed": np.array(seed), "theta_EB": np.array(0.045), "w1_EB": np.array(0.43),
+           "w2_EB": np.array(0.28), "sigma_EB": np.array(4.2), "xMAP": sc["xMAP"], "mse": arr(sc["mse"]),
+           "mu": arr(sc["mu"]), "calls": arr(it.globals.get("calls", np.zeros((1, 1))))}
+    # the same call again, keeping every output of SALSA_v2
+    it.run_source("[xM2, numA, numAt, objective, distance, times, mses] = SALSA_v2(y, A1, theta_EB*sigma_EB, 'MU', mu, "
+                  "'AT', AT1, 'StopCriterion', 1, 'True_x', x, 'ToleranceA', tol, 'MAXITERA', outeriters, 'Psi', Psi, "
+                  "'Phi', op.g, 'TVINITIALIZATION', 1, 'TViters', 10, 'LS', invLS, 'VERBOSE', 0);\n", sc)
+    for k in ("objective", "distance", "mses", "numA", "numAt"):
+        out[k] = arr(sc[k])
+    np.savez_compressed(os.path.join(HERE, "ref_salsa_gaussian.npz"), **out)
+    print("ref_salsa_gaussian.npz: outer iterations", np.ravel(out["objective"]).size - 1, "mse", float(np.ravel(out["mse"])[0]),
+          "calls", float(np.ravel(out["calls"])[0]))
+
+
 if __name__ == "__main__":
+    salsa()
+    if "--salsa-only" in sys.argv:
+        sys.exit(0)
     operators()
     for i, m in enumerate(("gaussian", "moffat", "laplace")):
         sapg(m, 100 + i)

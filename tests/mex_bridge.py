@@ -82,5 +82,27 @@ def make_sbd_mex(sbd):
             r["EB"] = row(o["EB"]); r["err_warm0"] = M(o["err_warm0"]); r["seconds"] = M(o["seconds"])
             r["last_samp"] = M(float(o["last_samp"]))
             return [r]
+        if cmd == "max_eigenval":
+            sz = _vec(a[0]).astype(int)
+            model, t, phi = int(_s(a[1])), int(_s(a[2])), _s(a[3])
+            x0 = np.asarray(a[7]) if len(a) > 7 and np.asarray(a[7]).size else None
+            v, k = H.engine_for((sz[0], sz[1]), t, model, phi).max_eigenval(psi_of(a[4]), _s(a[5]), int(_s(a[6])), x0=x0)
+            return [M(v), M(float(k))][:max(nargout, 1)]
+        if cmd == "observe":
+            x = np.asarray(a[0], dtype=np.float64)
+            model, t, phi = int(_s(a[1])), int(_s(a[2])), _s(a[3])
+            noise = np.asarray(a[6]) if len(a) > 6 and np.asarray(a[6]).size else None
+            y, sg, nr = H.engine_for(x.shape, t, model, phi).observe(x, psi_of(a[4]), _s(a[5]), noise=noise)
+            return [y, M(sg), M(nr)][:max(nargout, 1)]
+        if cmd == "salsa":
+            y = np.asarray(a[0], dtype=np.float64)
+            model, t, phi = int(_s(a[1])), int(_s(a[2])), _s(a[3])
+            xt = np.asarray(a[10]) if len(a) > 10 and np.asarray(a[10]).size else None
+            maxiter = int(_s(a[7]))
+            r = H.engine_for(y.shape, t, model, phi).salsa_tv(y, psi_of(a[4]), _s(a[5]), _s(a[6]), maxiter, _s(a[8]),
+                                                             int(_s(a[9])), x_true=xt)
+            pad = lambda v, n: np.concatenate([np.ravel(v), np.zeros(n - np.size(v))]).reshape(1, -1)
+            return [r["x"], pad(r["objective"], maxiter + 1), pad(r["distance"], maxiter), pad(r["mses"], maxiter + 1),
+                    M(float(r["n_outer"]))][:max(nargout, 1)]
         raise MatlabError(f"sbd_mex: unknown command {cmd}")
     return sbd_mex

@@ -160,3 +160,21 @@ def test_setup_stage_vs_reference_execution(sbd, name):
     # Philox start vector: converges to the same eigenvalue within the stop tolerance
     val2, _ = eng.max_eigenval(ev_psi, 1e-4, 10000, seed=3)
     assert abs(val2 - val) < 3e-2 * val      # the 1e-4 stop rule leaves a start-vector dependence of ~1%
+
+
+def test_salsa_map_vs_reference_execution(sbd):
+    """Post-SAPG MAP stage (SALSA_v2 with the TV prox warm start and the FFT least-squares step) on
+    the device vs run_Gaussian_demo.m:210-244 executed verbatim."""
+    g = dict(np.load(os.path.join(GOLDEN, "ref_salsa_gaussian.npz")))
+    x, y = g["x"], g["y"]
+    th, w1, w2, s2 = sc(g["theta_EB"]), sc(g["w1_EB"]), sc(g["w2_EB"]), sc(g["sigma_EB"])
+    eng = sbd.engine_for(x.shape, 7, 0, 0.0)
+    r = eng.salsa_tv(y, (w1, w2), th * s2, th / 10, maxiter=500, tolA=1e-5, tv_iters=10, x_true=x)
+    obj = np.ravel(g["objective"])
+    assert r["n_outer"] == obj.size - 1 and r["numA"] == sc(g["numA"])
+    assert rel(r["objective"], obj) < 1e-10
+    assert rel(r["x"], g["xMAP"]) < 1e-9
+    assert rel(r["distance"], np.ravel(g["distance"])) < 1e-8
+    assert rel(r["mses"], np.ravel(g["mses"])) < 1e-9
+    mse = 10 * np.log10(np.linalg.norm(x - r["x"], "fro") ** 2 / x.size)
+    assert abs(mse - sc(g["mse"])) < 1e-6

@@ -116,3 +116,31 @@ def test_sapg_wrappers_reproduce_the_reference(it, name):
                "laplace": ("theta_EB", "b_EB", "sigma_EB")}[name]
     for o in ref_out:
         assert np.isfinite(sc(scope[o]))
+
+
+def test_setup_and_map_wrappers(it):
+    """sbd_max_eigenval.m / sbd_observe.m / sbd_salsa_map.m executed as MATLAB source on the GPU box."""
+    from oracle.mlab.interp import M
+    g = dict(np.load(os.path.join(GOLDEN, "ref_sapg_gaussian.npz")))
+    rng = np.random.default_rng(int(sc(g["seed"])))
+    x0 = rng.standard_normal(g["x"].shape); noise = rng.standard_normal(g["x"].shape)
+    scope = {"x": g["x"], "x0": x0, "noise": noise}
+    it.run_source("""
+im_size = size(x);
+evMax = sbd_max_eigenval(0, im_size, 7, 0, [1 1], 1e-4, 1e4, x0);
+[y, sigma, nrm] = sbd_observe(x, 0, 7, 0, [0.4 0.3], 30, noise);
+""", scope)
+    assert abs(sc(scope["evMax"]) - sc(g["evMax"])) <= 1e-11 * sc(g["evMax"])
+    assert abs(sc(scope["sigma"]) - sc(g["op_sigma"])) <= 1e-12 * sc(g["op_sigma"])
+    assert rel(scope["y"], g["y"]) < 1e-12
+    s = dict(np.load(os.path.join(GOLDEN, "ref_salsa_gaussian.npz")))
+    scope = {"y": s["y"], "x": s["x"], "theta_EB": M(sc(s["theta_EB"])), "w1_EB": M(sc(s["w1_EB"])),
+             "w2_EB": M(sc(s["w2_EB"])), "sigma_EB": M(sc(s["sigma_EB"]))}
+    it.run_source("""
+mu = theta_EB/10;
+[xMAP, objective, distance, mses, n_outer] = sbd_salsa_map(y, 0, 7, 0, [w1_EB w2_EB], theta_EB*sigma_EB, mu, 500, 1e-5, 10, x);
+mse = 10*log10(norm(x-xMAP,'fro')^2 / numel(x));
+""", scope)
+    assert rel(scope["xMAP"], s["xMAP"]) < 1e-9
+    assert rel(np.ravel(scope["objective"]), np.ravel(s["objective"])) < 1e-10
+    assert abs(sc(scope["mse"]) - sc(s["mse"])) < 1e-6

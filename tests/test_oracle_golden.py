@@ -135,3 +135,28 @@ def test_sapg_run_matches_reference_execution(name):
     # every field the reference returns is also returned by the oracle (field names)
     ref_fields = {k[4:] for k in g if k.startswith("res_")}
     assert ref_fields <= set(r.keys())
+
+
+def test_salsa_map_matches_reference_execution():
+    """SALSA_v2 as the Gaussian demo calls it (run_Gaussian_demo.m:210-244, executed verbatim)."""
+    from oracle import salsa
+    g = dict(np.load(os.path.join(GOLDEN, "ref_salsa_gaussian.npz")))
+    x, y = g["x"], g["y"]
+    th, w1, w2, s2 = sc(g["theta_EB"]), sc(g["w1_EB"]), sc(g["w2_EB"]), sc(g["sigma_EB"])
+    cl = OP.gaussian_closures(x.shape, 7, 0.0)
+    A1 = lambda z: cl["A"](z, w1, w2)
+    AT1 = lambda z: cl["AT"](z, w1, w2)
+    mu = th / 10                                                    # run_Gaussian_demo.m:222
+    F = 1.0 / (np.abs(cl["H_FFT"](w1, w2)) ** 2 + mu)               # :224
+    invLS = lambda z: np.real(np.fft.ifft2(F * np.fft.fft2(z)))     # :225
+    Psi = lambda z, t: tv.chambolle_prox_TV_stop(z, "lambda", t, "maxiter", 25)[0]
+    out = salsa.SALSA_v2(y, A1, th * s2, "MU", mu, "AT", AT1, "StopCriterion", 1, "True_x", x, "ToleranceA", 1e-5,
+                         "MAXITERA", 500, "Psi", Psi, "Phi", tv.TVnorm, "TVINITIALIZATION", 1, "TViters", 10,
+                         "LS", invLS, "VERBOSE", 0)
+    assert rel(out[0], g["xMAP"]) < 1e-11
+    assert out[1] == sc(g["numA"]) and out[2] == sc(g["numAt"])
+    assert rel(out[3], np.ravel(g["objective"])) < 1e-12
+    assert rel(out[4], np.ravel(g["distance"])) < 1e-10
+    assert rel(out[6], np.ravel(g["mses"])) < 1e-11
+    mse = 10 * np.log10(np.linalg.norm(x - out[0], "fro") ** 2 / x.size)      # :244
+    assert abs(mse - sc(g["mse"])) < 1e-9
