@@ -216,16 +216,38 @@ __device__ __forceinline__ size_t spec_idx(const SpecGeom& g, int k, int q) {
 }
 
 // ---------------------------------------------------------------------------
+// L2 prefetch of what the block `pf` positions later in launch order will read.
+// The passes hold one to three blocks per SM and a block's first stage waits for
+// all its data (DRAM ~2000 cycles under load here), so the block that takes over
+// the SM one wave later should find its input in L2.  pf = resident blocks.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void l2_prefetch(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// contiguous region, one prefetch per 128-byte line
+__device__ __forceinline__ void l2_prefetch_span(const void* p, size_t bytes) {
+    const char* b = reinterpret_cast<const char*>(p);
+    for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)blockDim.x * 128) l2_prefetch(b + o);
+}
+
+// ---------------------------------------------------------------------------
 // rows pass, forward: real lines -> half spectra.  One block = LP line pairs.
 // grid = (ny/2/LP, batch), block = max(32, LP*N/16), smem = LP*fft_line_elems<N>()*16
 // ---------------------------------------------------------------------------
 template <int N>
 __global__ void k_rows_fwd(const double* __restrict__ x, double2* __restrict__ spec, SpecGeom sg, int LP,
-                           size_t img_stride, size_t spec_stride, const double2* __restrict__ tw) {
+                           size_t img_stride, size_t spec_stride, const double2* __restrict__ tw, int pf) {
     extern __shared__ double2 fsm[];
     constexpr int TL = N / 16, LE = fft_line_elems<N>();
     const int img = blockIdx.y;
     const int line0 = 2 * blockIdx.x * LP;
+    {
+        const unsigned int nxt = blockIdx.y * gridDim.x + blockIdx.x + pf;
+        if (pf > 0 && nxt < gridDim.x * gridDim.y) {
+            const unsigned int i2 = nxt / gridDim.x, b2 = nxt - i2 * gridDim.x;
+            l2_prefetch_span(x + (size_t)i2 * img_stride + (size_t)(2 * b2 * LP) * N, (size_t)2 * LP * N * sizeof(double));
+        }
+    }
     const bool active = threadIdx.x < LP * TL;
     const int b = threadIdx.x / TL, tl = threadIdx.x - b * TL;
     const double* xa = x + (size_t)img * img_stride + (size_t)(line0 + 2 * b) * N;
@@ -251,13 +273,27 @@ __global__ void k_rows_fwd(const double* __restrict__ x, double2* __restrict__ s
 // factor is folded into the spectral multiply of the column pass)
 template <int N>
 __global__ void k_rows_inv(const double2* __restrict__ spec, double* __restrict__ out, SpecGeom sg, int LP,
-                           size_t img_stride, size_t spec_stride, const double2* __restrict__ tw) {
+                           size_t img_stride, size_t spec_stride, const double2* __restrict__ tw, int pf) {
     extern __shared__ double2 fsm[];
     constexpr int TL = N / 16, LE = fft_line_elems<N>();
     const int img = blockIdx.y;
     const int line0 = 2 * blockIdx.x * LP;
     const double2* si = spec + (size_t)img * spec_stride;
     constexpr int HB = N / 2 + 1;
+    {
+        // the 2*LP lines of a block are one contiguous piece of 2*LP*C bins in every tile
+        const unsigned int nxt = blockIdx.y * gridDim.x + blockIdx.x + pf;
+        if (pf > 0 && nxt < gridDim.x * gridDim.y) {
+            const unsigned int i2 = nxt / gridDim.x, b2 = nxt - i2 * gridDim.x;
+            const double2* s2 = spec + (size_t)i2 * spec_stride;
+            const int piece = 2 * LP * sg.C * (int)sizeof(double2);
+            const int lpp = (piece + 127) / 128, ntile = (HB + sg.C - 1) >> sg.logC;
+            for (int e = threadIdx.x; e < ntile * lpp; e += blockDim.x) {
+                const int kt = e / lpp, l = e - kt * lpp;
+                l2_prefetch(reinterpret_cast<const char*>(s2 + spec_idx(sg, kt << sg.logC, 2 * b2 * LP)) + l * 128);
+            }
+        }
+    }
     for (int e = threadIdx.x; e < LP * HB; e += blockDim.x) {
         const int bb = e / HB, k = e - bb * HB;
         double2* L = fsm + (size_t)bb * LE;
@@ -305,7 +341,7 @@ __global__ void k_rows_inv(const double2* __restrict__ spec, double* __restrict_
 }
 
 // ---------------------------------------------------------------------------
-// column pass.  grid = (ntiles, batch); block = max(32, C*N/16);
+// column pass.  grid = (batch, ntiles*nsub); block = max(32, C*N/16);
 // dynamic smem = C*fft_line_elems<N>()*16 bytes.  Thread -> (tl, c), c fastest.
 // ---------------------------------------------------------------------------
 enum ColMode {
@@ -329,6 +365,7 @@ struct ColArgs {
     size_t spec_stride;
     int nk, nxfull, t, npsi, C, logC, opsel;   // C = columns per block
     int LC, nsub, ntiles;                      // layout tile width, blocks per tile, tiles per image
+    int pf;                                    // L2 prefetch distance in blocks (0 = off)
     double opscale;
     double mu;              // COL_FILTER: the ADMM penalty in 1/(|H|^2 + mu)   (run_Gaussian_demo.m:224)
 };
@@ -339,10 +376,31 @@ __global__ void k_cols(const ColArgs a) {
     __shared__ double2 coefS[8][3][MAXT];
     __shared__ double redS[3 * 32];
     constexpr int TL = N / 16;
-    const int img = blockIdx.y;
+    // grid = (batch, blocks per image): the images of a batch are neighbours in launch order, so the
+    // Y^ tile they all read comes from DRAM once and from L2 for the rest of the batch
+    const int img = blockIdx.x, bx = blockIdx.y;
     const int C = a.C, LC = a.LC;
-    const int tile = blockIdx.x / a.nsub, sub = blockIdx.x - tile * a.nsub;
+    const int tile = bx / a.nsub, sub = bx - tile * a.nsub;
     const int k0 = tile * LC + sub * C;
+    {
+        const unsigned int nxt = blockIdx.y * gridDim.x + blockIdx.x + a.pf;
+        if (a.pf > 0 && nxt < gridDim.x * gridDim.y) {
+            const unsigned int b2 = nxt / gridDim.x, i2 = nxt - b2 * gridDim.x;
+            const unsigned int t2 = b2 / a.nsub, s2 = b2 - t2 * a.nsub;
+            const size_t off2 = (size_t)t2 * N * LC + (size_t)s2 * C;
+            const double2* p2 = a.in + (size_t)i2 * a.spec_stride + off2;
+            const bool yh2 = (MODE == COL_MUL_INV || MODE == COL_FWD_REDUCE || MODE == COL_FILTER) && i2 == 0;   // once per batch
+            if (C == LC) {
+                l2_prefetch_span(p2, (size_t)N * C * sizeof(double2));
+                if (yh2) l2_prefetch_span(a.yhat + off2, (size_t)N * C * sizeof(double2));
+            } else {
+                for (int q = threadIdx.x; q < N; q += blockDim.x) {
+                    l2_prefetch(p2 + (size_t)q * LC);
+                    if (yh2) l2_prefetch(a.yhat + off2 + (size_t)q * LC);
+                }
+            }
+        }
+    }
     const size_t tile_off = (size_t)img * a.spec_stride + (size_t)tile * N * LC + (size_t)sub * C;
     const double2* in = a.in + tile_off;
     double2* out = a.out + tile_off;
@@ -472,12 +530,12 @@ __global__ void k_cols(const ColArgs a) {
 
     if (MODE == COL_FWD_REDUCE || MODE == COL_FILTER) {
         block_sum<3>(acc, redS);
-        const unsigned int ntiles = gridDim.x;
+        const unsigned int ntiles = gridDim.y;
         double* part = a.partials + (size_t)img * ntiles * 4;
         if (threadIdx.x == 0) {
-            part[blockIdx.x * 4 + 0] = acc[0];
-            part[blockIdx.x * 4 + 1] = acc[1];
-            part[blockIdx.x * 4 + 2] = acc[2];
+            part[bx * 4 + 0] = acc[0];
+            part[bx * 4 + 1] = acc[1];
+            part[bx * 4 + 2] = acc[2];
         }
         if (last_block_ticket(a.counters + img, ntiles)) {
             if (threadIdx.x < 32) {

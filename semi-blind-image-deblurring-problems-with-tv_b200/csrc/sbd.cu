@@ -73,6 +73,7 @@ struct sbd_ctx {
 
     // geometry
     int tvV = 1, tv_gx = 1, tv_gy = 1, tv_seg = 8, tv_parts = 1;
+    int sm_count = 148, fft_pf = 1;                                     // L2 prefetch distance of the FFT passes
     int cmT = 5, cm_strips = 1, cm_gx = 1, cm_gy = 1, cm_seg = 128;     // fused Chambolle geometry
     bool cm_pipe = false;
     double salsa_mu = 0.0;
@@ -361,6 +362,19 @@ void set_smem(K kernel, size_t bytes) {
     done[key] = bytes;
 }
 
+// blocks of `kernel` resident on the whole device = the L2 prefetch distance of the FFT passes
+template <typename K>
+int resident_blocks(sbd_ctx* c, K kernel, int threads, size_t smem) {
+    static std::map<std::pair<const void*, size_t>, int> cache;
+    const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), smem * 4096 + (size_t)threads);
+    auto it = cache.find(key);
+    if (it != cache.end()) return c->fft_pf ? it->second : 0;
+    int per_sm = 1;
+    SBD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    cache[key] = std::max(1, per_sm) * c->sm_count;
+    return c->fft_pf ? cache[key] : 0;
+}
+
 #define SBD_FFT_SIZES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
 
 SpecGeom spec_geom(const sbd_ctx* c) {
@@ -375,7 +389,8 @@ void rows_fwd(sbd_ctx* c, const double* x, double2* spec, int batch) {
     const SpecGeom sg = spec_geom(c);
     switch (c->nx) {
 #define X(N) case N: set_smem(k_rows_fwd<N>, smem); \
-        k_rows_fwd<N><<<g, c->rowsT, smem, c->stream>>>(x, spec, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
+        k_rows_fwd<N><<<g, c->rowsT, smem, c->stream>>>(x, spec, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx, \
+                                                        resident_blocks(c, k_rows_fwd<N>, c->rowsT, smem)); break;
         SBD_FFT_SIZES(X)
 #undef X
         default: throw Error{SBD_E_UNSUPPORTED, "rows_fwd: unsupported size"};
@@ -389,7 +404,8 @@ void rows_inv(sbd_ctx* c, const double2* spec, double* out, int batch) {
     const SpecGeom sg = spec_geom(c);
     switch (c->nx) {
 #define X(N) case N: set_smem(k_rows_inv<N>, smem); \
-        k_rows_inv<N><<<g, c->rowsT, smem, c->stream>>>(spec, out, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
+        k_rows_inv<N><<<g, c->rowsT, smem, c->stream>>>(spec, out, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx, \
+                                                        resident_blocks(c, k_rows_inv<N>, c->rowsT, smem)); break;
         SBD_FFT_SIZES(X)
 #undef X
         default: throw Error{SBD_E_UNSUPPORTED, "rows_inv: unsupported size"};
@@ -408,9 +424,9 @@ void cols(sbd_ctx* c, const double2* in, double2* out, int batch, int opsel = 0)
     a.opscale = 1.0 / ((double)c->nx * (double)c->ny);
     a.mu = c->salsa_mu;
     const size_t smem = c->cols_smem;
-    dim3 g(c->ntiles * (c->colsC / c->colsKC), batch);
+    dim3 g(batch, c->ntiles * (c->colsC / c->colsKC));
     switch (c->ny) {
-#define X(N) case N: set_smem(k_cols<N, MODE>, smem); \
+#define X(N) case N: set_smem(k_cols<N, MODE>, smem); a.pf = resident_blocks(c, k_cols<N, MODE>, c->colsT, smem); \
         k_cols<N, MODE><<<g, c->colsT, smem, c->stream>>>(a); break;
         SBD_FFT_SIZES(X)
 #undef X
@@ -534,6 +550,12 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
         c->spec_elems = (size_t)c->ntiles * cols * c->colsC;
         c->profile = getenv("SBD_PROFILE") && atoi(getenv("SBD_PROFILE")) != 0;
         SBD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        {
+            int dev = 0;
+            SBD_CUDA(cudaGetDevice(&dev));
+            SBD_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
+            if (const char* e = getenv("SBD_FFT_PF")) c->fft_pf = atoi(e);
+        }
         c->taps = dalloc<double>(3 * MAXT * MAXT);
         c->ctl = dalloc<Control>(1);
         c->psi_dev = dalloc<double>(2);

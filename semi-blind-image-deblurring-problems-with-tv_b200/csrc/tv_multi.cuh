@@ -34,18 +34,17 @@ __device__ __forceinline__ double fast_rcp_seed(double a) {
 // first (2^-20) sqrt estimate so that its MUFU latency overlaps the refinement.
 __device__ __forceinline__ void fast_sqrt_rcp(double a, double tau, double& tmp, double& rinv) {
     const double y = fast_rsqrt_seed(a + 1e-300);
-    double g = a * y, h = 0.5 * y;
+    double g = a * y;
+    const double h = 0.5 * y;
     double rs = fast_rcp_seed(fma(tau, g, 1.0));
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g); h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    // (one Goldschmidt step + a residual correction needs two fp64 ops fewer but measured 3% slower)
+    // third-order steps: same dependency depth as two second-order ones, two fp64 ops fewer.
+    // y = (1+dl)/sqrt(a)  =>  r = 0.5 - g*h = -(dl + dl^2/2),  1/(1+dl) = 1 + r + 1.5 r^2 + O(r^3)
+    const double r = fma(-g, h, 0.5);
+    const double t = r * fma(r, 1.5, 1.0);
+    g = fma(g, t, g);                               // |rel err| ~ 2.5 |r|^3 < 2^-60
     const double d = fma(tau, g, 1.0);
-    double e = fma(-d, rs, 1.0);
-    rs = fma(rs, e, rs);
-    e = fma(-d, rs, 1.0);           // the seed is 1/d to ~2^-19 (seed error + d known to 2^-20):
-    rs = fma(rs, e, rs);            // two Newton steps reach 2^-38 and 2^-76
+    const double e = fma(-d, rs, 1.0);              // the seed is 1/d to ~2^-19 (seed error + d known to 2^-20)
+    rs = fma(rs, fma(e, e, e), rs);                 // 1/d = rs (1 + e + e^2 + O(e^3)): ~2^-57
     tmp = g; rinv = rs;
 }
 
@@ -199,6 +198,22 @@ __device__ __forceinline__ void cm_generic_iter(int r, CmLv (&h)[T], CmPk (&inbo
     }
 }
 
+// L2 prefetch of the rows the march will load CM_PF rows from now.  ptxas schedules the first use of a
+// loaded register a fixed ~180 instructions behind the load whatever the source order says, which
+// covers an L2 hit but not the ~2000 cycles a DRAM access takes here (ncu: 24 % of the samples were
+// long_scoreboard on those two uses); the prefetch turns the loads into L2 hits without registers.
+constexpr int CM_PF = 3;            // distances 1..8 measure the same, 16 is slower
+template <bool EDGE, bool ZERO>
+__device__ __forceinline__ void cm_prefetch(const double* __restrict__ g, const double* __restrict__ px,
+                                            const double* __restrict__ py, size_t off, const CmLane& L) {
+    if (EDGE && !L.in0) return;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + off));
+    if (!ZERO) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(px + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(py + off));
+    }
+}
+
 // The march of one warp.  nlev <= T levels are applied.
 template <int T, bool EDGE, bool PIPE, bool ZERO>
 __device__ __forceinline__ void cm_march(const double* __restrict__ g, const double* __restrict__ pxi,
@@ -248,8 +263,10 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
         if (r <= fast_hi) {
             CmPk nA = nxt, nB;
             while (r + 1 <= fast_hi) {
+                cm_prefetch<EDGE, ZERO>(g, pxi, pyi, (size_t)((long long)min(r + 1 + CM_PF, ny - 1) * nx + ibase), L);
                 cm_load<EDGE, ZERO>(nB, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L);
                 fast_body(nA, r);
+                cm_prefetch<EDGE, ZERO>(g, pxi, pyi, (size_t)((long long)min(r + 2 + CM_PF, ny - 1) * nx + ibase), L);
                 cm_load<EDGE, ZERO>(nA, g, pxi, pyi, (size_t)((long long)(r + 2) * nx + ibase), L);
                 fast_body(nB, r + 1);
                 r += 2;

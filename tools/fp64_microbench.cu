@@ -45,7 +45,8 @@ void run(const char* name, int warps_per_sm) {
 
 int main() {
     run<1, 0>("DFMA", 4);  run<1, 0>("DFMA", 8);  run<1, 0>("DFMA", 16); run<1, 0>("DFMA", 32); run<1, 0>("DFMA", 64);
-    run<2, 0>("DFMA", 8);  run<2, 0>("DFMA", 12); run<2, 0>("DFMA", 16);
+    run<2, 0>("DFMA", 8);  run<2, 0>("DFMA", 12); run<2, 0>("DFMA", 16); run<2, 0>("DFMA", 20); run<2, 0>("DFMA", 24); run<2, 0>("DFMA", 32);
+    run<3, 0>("DFMA", 12); run<4, 0>("DFMA", 12); run<6, 0>("DFMA", 8); run<6, 0>("DFMA", 12);
     run<4, 0>("DFMA", 4);  run<4, 0>("DFMA", 8);  run<4, 0>("DFMA", 16); run<8, 0>("DFMA", 16); run<8, 0>("DFMA", 32);
     run<8, 1>("DADD", 16); run<8, 2>("DMUL", 16);
     return 0;
