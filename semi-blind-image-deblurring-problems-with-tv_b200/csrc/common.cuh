@@ -50,7 +50,7 @@ struct ChambState {             // one per image / chain
     unsigned int counter;       // last-block-done ticket
     int redo;                   // fused kernel: number of levels the redo launch must apply (0 = none)
     int buf;                    // which buffer of the ping-pong pair holds the current dual pair
-    int pad;
+    int emitted;                // fused kernel: the prox output f was written by the final sweep block
 };
 
 struct SapgConst {              // constants of a run (device copy)

@@ -75,7 +75,7 @@ struct sbd_ctx {
     int tvV = 1, tv_gx = 1, tv_gy = 1, tv_seg = 8, tv_parts = 1;
     int sm_count = 148, fft_pf = 1;                                     // L2 prefetch distance of the FFT passes
     int cmT = 5, cm_strips = 1, cm_gx = 1, cm_gy = 1, cm_seg = 128;     // fused Chambolle geometry
-    bool cm_pipe = false;
+    bool cm_pipe = false, cm_emit = true;
     double salsa_mu = 0.0;
     int cm_minb = 3;
     int rowsLP = 1, rowsT = 32, colsC = 2, colsLogC = 1, colsT = 32, ntiles = 1;
@@ -180,6 +180,7 @@ void set_geometry(sbd_ctx* c, int batch) {
         int sg = 128;
         while (sg > 8 && (long long)c->cm_gx * ((ny + sg - 1) / sg) * batch < 6 * 148) sg /= 2;
         if (const char* e = getenv("SBD_CHAMB_SEG")) sg = std::max(1, atoi(e));
+        if (const char* e = getenv("SBD_CHAMB_EMIT")) c->cm_emit = atoi(e) != 0;
         c->cm_seg = sg;
         c->cm_gy = (ny + sg - 1) / sg;
     }
@@ -275,24 +276,24 @@ void zero_duals(sbd_ctx* c, int batch) {
     SBD_CUDA(cudaMemsetAsync(c->py0, 0, sizeof(double) * batch * c->npix, c->stream));
 }
 
-template <int T, bool PIPE, int MINB>
+template <int T, bool PIPE, int MINB, int EMIT = 0>
 void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const double* pyi, double* pxo,
-                        double* pyo, int batch, int redo, int zero_in) {
-    // strip geometry depends on the number of fused levels (lateral halo HL, 64 - 2*HL outputs per strip)
+                        double* pyo, int batch, int redo, int zero_in, double* f = nullptr) {
+    // strip geometry depends on the number of fused levels (lateral halo HL)
     constexpr int HL = (T + 1) & ~1, WO = 64 - 2 * HL;
     const int strips = (c->nx + WO - 1) / WO;
     dim3 grid((strips + TV_WARPS - 1) / TV_WARPS, c->cm_gy, batch);
     if (zero_in)
-        k_chamb_multi<T, PIPE, MINB, true><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
-                                                                                strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
+        k_chamb_multi<T, PIPE, MINB, true, EMIT><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
+                                                                                      strips, c->npix, c->ctl, c->chst, c->part_ch, redo, f);
     else
-        k_chamb_multi<T, PIPE, MINB, false><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
-                                                                                 strips, c->npix, c->ctl, c->chst, c->part_ch, redo);
+        k_chamb_multi<T, PIPE, MINB, false, EMIT><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
+                                                                                       strips, c->npix, c->ctl, c->chst, c->part_ch, redo, f);
 }
 
 // zero_start: the dual pair starts from zero (px0/py0 are then neither read nor need to be cleared
 // when the fused kernel runs; the single-sweep path clears them itself)
-void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, bool zero_start) {
+void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, bool zero_start, bool keep_duals = true) {
     k_chamb_reset<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->chst, batch);
     LAUNCH_CHECK(c);
     dim3 grid(c->tv_gx, c->tv_gy, batch);
@@ -305,8 +306,8 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
         if (c->cmT == 4) {
             const int a = maxiter / 4, r = maxiter % 4;
             if (a > 0 && r <= a) {
-                for (int i = 0; i < r; ++i) plan.push_back(5);
                 for (int i = 0; i < a - r; ++i) plan.push_back(4);
+                for (int i = 0; i < r; ++i) plan.push_back(5);      // a 5-level block last: it can emit f
             } else {
                 for (int i = 0; i < a; ++i) plan.push_back(4);
                 if (r) plan.push_back(4);           // kernel applies min(4, remaining) levels
@@ -320,9 +321,14 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
             const double* pyi = (b & 1) ? c->py1 : c->py0;
             double* pxo = (b & 1) ? c->px0 : c->px1;
             double* pyo = (b & 1) ? c->py0 : c->py1;
+            // the last planned block writes the prox output itself when it has the lateral slack (T = 5)
+            const bool emit = (b + 1 == plan.size()) && T == 5 && c->cm_emit;
             for (int redo = 0; redo < 2; ++redo) {
                 const int zin = (zero_start && b == 0) ? 1 : 0;
-                if (T == 3) chamb_multi_launch<3, false, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
+                if (emit && redo == 0) {
+                    if (keep_duals) chamb_multi_launch<5, false, 2, 1>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin, f);
+                    else chamb_multi_launch<5, false, 2, 2>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin, f);
+                } else if (T == 3) chamb_multi_launch<3, false, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
                 else if (T == 5) chamb_multi_launch<5, false, 2>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
                 else chamb_multi_launch<4, false, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
                 LAUNCH_CHECK(c);
@@ -721,7 +727,7 @@ int sbd_tvprox_dev(sbd_ctx* c, const double* d_g, double lambda, int maxiter, do
     SBD_CUDA(cudaSetDevice(c->device));
     ensure_ws(c, batch);
     set_chamb_options(c, lambda, maxiter, tol, tau);
-    chambolle(c, d_g, d_f, batch, maxiter, true);
+    chambolle(c, d_g, d_f, batch, maxiter, true, false);
     fetch_chamb_state(c, batch, iters, err);
     SBD_CATCH(c)
 }
@@ -744,7 +750,7 @@ int sbd_tvprox(sbd_ctx* c, const double* g, double lambda, int maxiter, double t
         SBD_CUDA(cudaMemcpyAsync(c->px0, dual_px, bytes, cudaMemcpyHostToDevice, c->stream));
         SBD_CUDA(cudaMemcpyAsync(c->py0, dual_py, bytes, cudaMemcpyHostToDevice, c->stream));
     }
-    chambolle(c, c->X, c->P, batch, maxiter, dual_px == nullptr);
+    chambolle(c, c->X, c->P, batch, maxiter, dual_px == nullptr, px != nullptr || py != nullptr);
     SBD_CUDA(cudaMemcpyAsync(f, c->P, bytes, cudaMemcpyDeviceToHost, c->stream));
     std::vector<ChambState> h(batch);
     SBD_CUDA(cudaMemcpyAsync(h.data(), c->chst, sizeof(ChambState) * batch, cudaMemcpyDeviceToHost, c->stream));
@@ -1135,7 +1141,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     const double* gstats = nullptr;
     auto prox = [&]() {
         PhaseTimer pt(c, 3);
-        chambolle(c, c->X, c->P, nch, prm->chambolle_maxiter, true);    // zero start: chambolle_prox_TV_stop.m:68-69
+        chambolle(c, c->X, c->P, nch, prm->chambolle_maxiter, true, false);    // zero start: chambolle_prox_TV_stop.m:68-69
     };
     auto myula_step = [&]() {
         { PhaseTimer pt(c, 0);

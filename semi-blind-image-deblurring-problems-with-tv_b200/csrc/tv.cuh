@@ -262,6 +262,7 @@ k_chamb_out(const double* __restrict__ g, const double* __restrict__ px0,
             const double* __restrict__ py1, double* __restrict__ f, int nx, int ny, int seg,
             size_t img_stride, const Control* __restrict__ ctl, const ChambState* __restrict__ st) {
     const int img = blockIdx.z;
+    if (st[img].emitted) return;                    // the last fused block wrote f already (tv_multi.cuh)
     const StripGeom s = strip_geom<V>(nx, ny, seg);
     if (!s.warp_on) return;
     const double lambda = ctl->prox_lambda_theta;
@@ -299,7 +300,7 @@ k_chamb_out(const double* __restrict__ g, const double* __restrict__ px0,
 
 __global__ void k_chamb_reset(ChambState* st, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { st[i].k = 0; st[i].done = 0; st[i].err = 0.0; st[i].counter = 0u; st[i].redo = 0; st[i].buf = 0; }
+    if (i < n) { st[i].k = 0; st[i].done = 0; st[i].err = 0.0; st[i].counter = 0u; st[i].redo = 0; st[i].buf = 0; st[i].emitted = 0; }
 }
 
 }  // namespace sbd

@@ -13,6 +13,14 @@
 // the kernel for each of the T sweeps in order (speculation): if it fires at
 // sweep s < T the block is re-run from the same input with s levels ("redo"
 // launch, a no-op otherwise), so the result is exactly the reference's.
+//
+// EMIT: the block that is planned to be the last one also forms the prox output
+// f = g - lambda*div p (chambolle_prox_TV_stop.m:134) from the rows its top level
+// emits, instead of a separate pass over (g, px, py).  div p needs p one pixel to
+// the left and one row above the emitted row, so this needs one pixel of lateral
+// validity to spare (HL > nlev: the 5-level kernel has it) and the march starts
+// one row earlier.  EMIT = 2 additionally skips the store of the dual pair (the
+// SAPG loop starts every prox from zero and never reads it back).
 #pragma once
 #include "common.cuh"
 #include "tv.cuh"
@@ -141,6 +149,35 @@ __device__ __forceinline__ void cm_store(const CmPk& p, double* __restrict__ pxo
     }
 }
 
+// prox output of an emitted (final) row; prevpy = py of the row above (0 above the image)
+template <bool EDGE, int EMIT>
+__device__ __forceinline__ void cm_emit(const CmPk& p, double (&prevpy)[2], double* __restrict__ f,
+                                        double* __restrict__ pxo, double* __restrict__ pyo, size_t off,
+                                        const CmLane& L, double lambda, bool inseg, bool lastrow) {
+    const double pxl = shfl_up_d(p.px[1], 1);
+    double ux0 = p.px[0] - pxl, ux1 = p.px[1] - p.px[0];
+    if (EDGE) {
+        if (L.last0) ux0 = -p.px[0];
+        if (L.last1) ux1 = -p.px[1];
+    }
+    double uy0 = p.py[0] - prevpy[0], uy1 = p.py[1] - prevpy[1];
+    if (lastrow) { uy0 = -p.py[0]; uy1 = -p.py[1]; }
+    prevpy[0] = p.py[0]; prevpy[1] = p.py[1];
+    if (!inseg || !L.central) return;
+    // p.g carries g / lambda
+    const double f0 = fma(-lambda, uy0 + ux0, p.g[0] * lambda), f1 = fma(-lambda, uy1 + ux1, p.g[1] * lambda);
+    if (!EDGE) {
+        *reinterpret_cast<double2*>(f + off) = make_double2(f0, f1);
+        if (EMIT == 1) {
+            *reinterpret_cast<double2*>(pxo + off) = make_double2(p.px[0], p.px[1]);
+            *reinterpret_cast<double2*>(pyo + off) = make_double2(p.py[0], p.py[1]);
+        }
+    } else {
+        if (L.in0) { f[off] = f0; if (EMIT == 1) { pxo[off] = p.px[0]; pyo[off] = p.py[0]; } }
+        if (L.in1) { f[off + 1] = f1; if (EMIT == 1) { pxo[off + 1] = p.px[1]; pyo[off + 1] = p.py[1]; } }
+    }
+}
+
 // Schedule.  PIPE = false: in iteration r level s receives row r - s, which level
 // s-1 emitted earlier in the same iteration (levels run bottom-up, one dependent
 // chain).  PIPE = true: the levels are software-pipelined - level s consumes the
@@ -154,13 +191,14 @@ __device__ __forceinline__ void cm_take(CmPk& dst, const CmPk& raw, double invla
 }
 
 // One generic iteration of the march: honours all row flags, any nlev <= T.
-template <int T, bool EDGE, bool PIPE, bool ZERO>
+template <int T, bool EDGE, bool PIPE, bool ZERO, int EMIT>
 __device__ __forceinline__ void cm_generic_iter(int r, CmLv (&h)[T], CmPk (&inbox)[T], CmPk& nxt, double (&err)[T],
                                                 const double* __restrict__ g, const double* __restrict__ pxi,
                                                 const double* __restrict__ pyi, double* __restrict__ pxo,
                                                 double* __restrict__ pyo, int nx, int ny, int j0, int jlast,
                                                 int r0, long long ibase, const CmLane& L,
-                                                double invlam, double tau, int nlev) {
+                                                double invlam, double tau, int nlev,
+                                                double* __restrict__ f, double lambda, double (&prevpy)[2]) {
     constexpr int D = PIPE ? 2 : 1;
     CmPk loc[T];                                    // PIPE = false: rows only travel within the iteration
 #define CM_BOX(s_) (PIPE ? inbox[s_] : loc[s_])
@@ -189,7 +227,8 @@ __device__ __forceinline__ void cm_generic_iter(int r, CmLv (&h)[T], CmPk (&inbo
                 const bool inseg = hr >= j0 && hr <= jlast;
                 if (inseg) err[s] += e;
                 if (s + 1 == nlev) {
-                    if (inseg) cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)hr * nx + ibase), L);
+                    if (EMIT) cm_emit<EDGE, EMIT>(p, prevpy, f, pxo, pyo, (size_t)((long long)hr * nx + ibase), L, lambda, inseg, hr == ny - 1);
+                    else if (inseg) cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)hr * nx + ibase), L);
                 } else if (s + 1 < T) {
                     CM_BOX(s + 1) = p;
                 }
@@ -215,12 +254,12 @@ __device__ __forceinline__ void cm_prefetch(const double* __restrict__ g, const 
 }
 
 // The march of one warp.  nlev <= T levels are applied.
-template <int T, bool EDGE, bool PIPE, bool ZERO>
+template <int T, bool EDGE, bool PIPE, bool ZERO, int EMIT>
 __device__ __forceinline__ void cm_march(const double* __restrict__ g, const double* __restrict__ pxi,
                                          const double* __restrict__ pyi, double* __restrict__ pxo,
                                          double* __restrict__ pyo, int nx, int ny, int j0, int j1,
                                          const CmLane& L, double invlam, double tau, int nlev,
-                                         double (&err)[T]) {
+                                         double (&err)[T], double* __restrict__ f, double lambda) {
     constexpr int D = PIPE ? 2 : 1;
     CmLv h[T];
     CmPk inbox[T];
@@ -232,7 +271,8 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
             inbox[s].px[v] = 0.0; inbox[s].py[v] = 0.0; inbox[s].g[v] = 0.0;
         }
     }
-    const int r0 = max(j0 - nlev, 0);
+    const int r0 = max(j0 - nlev - (EMIT ? 1 : 0), 0);     // EMIT: the final row above the segment is needed too
+    double prevpy[2] = {0.0, 0.0};
     const int jlast = min(j1 - 1, ny - 1);          // last output row of this segment
     const int rend = jlast + D * (nlev - 1) + 1;    // last iteration (level nlev-1 receives row jlast+1)
     const long long ibase = L.i;
@@ -244,7 +284,7 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
         // steady state: every level live, interior rows only, every updated row inside the segment
         const int fast_lo = j0 + D * (T - 1) + 1, fast_hi = min(j1, ny - 2);
         for (; r < min(fast_lo, rend + 1); ++r)
-            cm_generic_iter<T, EDGE, PIPE, ZERO>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev);
+            cm_generic_iter<T, EDGE, PIPE, ZERO, EMIT>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev, f, lambda, prevpy);
         // Two rows per trip with two named prefetch buffers: the row loaded during one half is
         // first touched in the next half, a full level-sweep later, and no register rotation
         // (which the compiler would schedule right behind the load) is needed.
@@ -256,8 +296,11 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
                 const int s = PIPE ? T - 1 - q : q;
                 CmPk p = CM_BOX(s);
                 cm_step<EDGE, false>(h[s], p, L, tau, err[s], false, false, true);
-                if (s == T - 1) cm_store<EDGE>(p, pxo, pyo, (size_t)((long long)(rr - D * (T - 1) - 1) * nx + ibase), L);
-                else CM_BOX(s + 1) = p;
+                if (s == T - 1) {
+                    const size_t o = (size_t)((long long)(rr - D * (T - 1) - 1) * nx + ibase);
+                    if (EMIT) cm_emit<EDGE, EMIT>(p, prevpy, f, pxo, pyo, o, L, lambda, true, false);
+                    else cm_store<EDGE>(p, pxo, pyo, o, L);
+                } else CM_BOX(s + 1) = p;
             }
         };
         if (r <= fast_hi) {
@@ -275,18 +318,19 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
         }
     }
     for (; r <= rend; ++r)
-        cm_generic_iter<T, EDGE, PIPE, ZERO>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev);
+        cm_generic_iter<T, EDGE, PIPE, ZERO, EMIT>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev, f, lambda, prevpy);
 }
 
 // grid = (ceil(nstrips / TV_WARPS), nsegs, batch); block = TV_THREADS.
 // redo == 0: main launch of a block of T sweeps; redo == 1: re-run with the
 // number of levels the stop test asked for (no-op unless st.redo != 0).
-template <int T, bool PIPE, int MINB, bool ZERO>
+template <int T, bool PIPE, int MINB, bool ZERO, int EMIT>
 __global__ void __launch_bounds__(TV_THREADS, MINB)
 k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, const double* __restrict__ pyi,
               double* __restrict__ pxo, double* __restrict__ pyo, int nx, int ny, int seg, int nstrips,
               size_t img_stride, const Control* __restrict__ ctl, ChambState* __restrict__ st,
-              double* __restrict__ partials, int redo) {
+              double* __restrict__ partials, int redo, double* __restrict__ f) {
+    static_assert(EMIT == 0 || ((T + 1) & ~1) > T, "EMIT needs a spare pixel of lateral validity");
     constexpr int HL = (T + 1) & ~1;
     constexpr int WO = 64 - 2 * HL;
     __shared__ double sm[T * 32];
@@ -304,6 +348,7 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
     const double invlam = 1.0 / lambda;
     const size_t off = (size_t)img * img_stride;
     g += off; pxi += off; pyi += off; pxo += off; pyo += off;
+    if (EMIT) f += off;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strip = blockIdx.x * TV_WARPS + warp;
@@ -320,8 +365,8 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
         L.central = cen && (L.in0 || L.in1);
         const int j0 = blockIdx.y * seg, j1 = min(j0 + seg, ny);
         const bool edge = (i0 < 0) || (i0 + 64 > nx);
-        if (edge) cm_march<T, true, PIPE, ZERO>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
-        else      cm_march<T, false, PIPE, ZERO>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err);
+        if (edge) cm_march<T, true, PIPE, ZERO, EMIT>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err, f, lambda);
+        else      cm_march<T, false, PIPE, ZERO, EMIT>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err, f, lambda);
     }
 
     block_sum<T>(err, sm);
@@ -355,6 +400,7 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
                         S->k = k0 + nlev; S->err = elast; S->buf ^= 1;
                     } else if (stop == nlev) {      // stops exactly at the end of this block
                         S->k = k0 + nlev; S->err = estop; S->done = 1; S->buf ^= 1;
+                        if (EMIT) S->emitted = 1;   // f written above is the prox output
                     } else {                        // stopped inside the block: redo with `stop` levels
                         S->err = estop; S->redo = stop;
                     }

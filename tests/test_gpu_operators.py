@@ -184,6 +184,47 @@ def test_chambolle_batch_independent_stops(sbd, O):
     eng.close()
 
 
+@pytest.mark.parametrize("shape", [(128, 128), (130, 70)])
+def test_chambolle_stop_inside_every_block_position(sbd, O, shape):
+    """The last fused block writes the prox output itself; a stop test firing before, inside or exactly
+    at the end of that block must still give the reference's f, sweep count and dual pair."""
+    rng = np.random.default_rng(5)
+    g = rng.uniform(0, 255, shape)
+    eng = sbd.host._tv_engine(shape)
+    for kstop in (16, 19, 20, 21, 22, 23, 24, 25):
+        _, _, _, _, e_k = O.tv.chambolle_prox_TV_stop(g, "lambda", 0.3, "maxiter", kstop, "tol", 0.0, return_info=True)
+        tol = e_k * (1 + 1e-9)                       # err_k <= tol < err_(k-1): stops after sweep kstop
+        fo, pxo, pyo, ko, eo = O.tv.chambolle_prox_TV_stop(g, "lambda", 0.3, "maxiter", 25, "tol", tol, return_info=True)
+        assert ko == kstop
+        f, px, py, k, err = eng.tvprox(g, 0.3, 25, tol=tol)
+        assert k == ko and rel(f, fo) < TOL and rel(px, pxo) < 1e-11 and rel(py, pyo) < 1e-11
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (256, 256), (130, 70)])
+def test_chambolle_device_entry_without_duals(sbd, O, shape):
+    """sbd_tvprox_dev (device pointers, dual pair not kept): the path the SAPG loop uses."""
+    import ctypes as C
+    import torch
+    from sbd_b200._lib import lib
+    rng = np.random.default_rng(9)
+    g = rng.uniform(0, 255, (2,) + shape)
+    eng = sbd.Engine(shape[0], shape[1], 1, 0, 0.0, max_batch=2)
+    # column-major images on the device = transposed C-order tensors
+    gd = torch.from_numpy(np.ascontiguousarray(g.transpose(0, 2, 1))).cuda()
+    fd = torch.empty_like(gd)
+    it = (C.c_int * 2)()
+    er = (C.c_double * 2)()
+    for maxiter in (25, 20, 7):
+        rc = lib.sbd_tvprox_dev(eng._h, gd.data_ptr(), 0.8, maxiter, 1e-3, 0.249, fd.data_ptr(), it, er, 2)
+        assert rc == 0, lib.sbd_last_error(eng._h)
+        lib.sbd_synchronize(eng._h)
+        f = fd.cpu().numpy().transpose(0, 2, 1)
+        for b in range(2):
+            fo, _, _, ko, eo = O.tv.chambolle_prox_TV_stop(g[b], "lambda", 0.8, "maxiter", maxiter, "tol", 1e-3, return_info=True)
+            assert it[b] == ko and rel(f[b], fo) < TOL
+    eng.close()
+
+
 @pytest.mark.parametrize("n", [4096])
 def test_chambolle_large_properties(sbd, n):
     eng = sbd.host._tv_engine((n, n))
