@@ -358,6 +358,7 @@ struct ColArgs {
     const double2* yhat;    // Y^ (shared by all images of the batch)
     const double2* coef;    // PSF column coefficients [3][nk][MAXT]
     const double2* tw;      // twiddles of size N (this pass)
+    const double2* tw_x;    // twiddles of the rows pass (size nxfull): wk of the point-symmetric PSF form
     const Control* ctl;
     double* partials;       // [batch][ntiles][4]
     unsigned int* counters; // [batch]
@@ -371,7 +372,7 @@ struct ColArgs {
 };
 
 template <int N, int MODE>
-__global__ void k_cols(const ColArgs a) {
+__global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
     extern __shared__ double2 fsm[];
     __shared__ double2 coefS[8][3][MAXT];
     __shared__ double redS[3 * 32];
@@ -410,9 +411,18 @@ __global__ void k_cols(const ColArgs a) {
         for (int e = threadIdx.x; e < C * 3 * a.t; e += blockDim.x) {
             const int j = e % a.t, m = (e / a.t) % 3, c = e / (3 * a.t);
             const int k = min(k0 + c, a.nk - 1);
-            coefS[c][m][j] = __ldg(a.coef + ((size_t)m * a.nk + k) * MAXT + j);
+            const double2* cf = a.coef + ((size_t)m * a.nk + k) * MAXT;
+            if (a.t == 7) {                          // point-symmetric form, see psf_sym3
+                const double2 wk = __ldg(a.tw_x + k);
+                const double2 wk3 = cmul(cmul(wk, wk), wk);
+                if (j <= 3) coefS[c][m][j] = psf_sym3_coef(cf, make_double2(wk3.x, -wk3.y), j);
+                else if (j == 4) coefS[c][m][j] = wk3;
+            } else {
+                coefS[c][m][j] = __ldg(cf + j);
+            }
         }
     }
+    const bool sym = a.t == 7;
     __syncthreads();
 
     const bool active = threadIdx.x < C * TL;
@@ -421,12 +431,21 @@ __global__ void k_cols(const ColArgs a) {
     const bool kin = k < a.nk;                       // the last tile may be partly empty
     double2* line = fsm + c;                         // element stride C between positions
     double acc[3] = {0.0, 0.0, 0.0};
+    auto kern = [&](int m, double2 w) {              // K^[k, q] of kernel m (0: h, 1: dh/dpsi0, 2: dh/dpsi1)
+        if (sym) {
+            const PsfW3 p = psf_w3(w);
+            const double2 ph = cmul(coefS[c][0][4], p.w3);         // (wk w)^3
+            const double sv = psf_sym3(coefS[c][m], p);
+            return make_double2(sv * ph.x, sv * ph.y);
+        }
+        return psf_horner(coefS[c][m], a.t, w);
+    };
 
     auto gsrc = [&](int q) {
         double2 v = __ldg(in + (size_t)q * LC + c);
         if (MODE == COL_MUL_INV) {
             const double2 w = __ldg(a.tw + q);
-            const double2 H = psf_horner(coefS[c][0], a.t, w);
+            const double2 H = kern(0, w);
             const double2 yv = __ldg(yh + (size_t)q * LC + c);
             const double2 R = csub(cmul(H, v), yv);                 // H X^ - Y^
             const double2 G = cmulc(R, H);                          // conj(H) R
@@ -441,17 +460,26 @@ __global__ void k_cols(const ColArgs a) {
         if (MODE == COL_FWD_REDUCE) {
             const double2 w = __ldg(a.tw + q);
             const double2 yv = __ldg(yh + (size_t)q * LC + c);
-            const double2 H = psf_horner(coefS[c][0], a.t, w);
-            const double2 R = csub(cmul(H, v), yv);
             // Hermitian weights of the half spectrum: interior bins count twice
             const double wt = (k == 0 || 2 * k == a.nxfull) ? 1.0 : 2.0;
-            acc[0] += wt * (R.x * R.x + R.y * R.y);
-            const double2 T0 = cmul(psf_horner(coefS[c][1], a.t, w), v);
-            acc[1] += wt * (T0.x * R.x + T0.y * R.y);               // Re conj(D0 X^) R
-            if (a.npsi > 1) {
-                const double2 T1 = cmul(psf_horner(coefS[c][2], a.t, w), v);
-                acc[2] += wt * (T1.x * R.x + T1.y * R.y);
+            double2 R, T0, T1 = make_double2(0.0, 0.0);
+            if (sym) {
+                // the common factor (wk w)^3 of the three kernels is applied to X^ once; what is left of
+                // each kernel is a real number
+                const PsfW3 p = psf_w3(w);
+                const double2 xr = cmul(cmul(coefS[c][0][4], p.w3), v);
+                const double sh = psf_sym3(coefS[c][0], p), s0 = psf_sym3(coefS[c][1], p);
+                R = make_double2(fma(sh, xr.x, -yv.x), fma(sh, xr.y, -yv.y));
+                T0 = make_double2(s0 * xr.x, s0 * xr.y);
+                if (a.npsi > 1) { const double s1 = psf_sym3(coefS[c][2], p); T1 = make_double2(s1 * xr.x, s1 * xr.y); }
+            } else {
+                R = csub(cmul(psf_horner(coefS[c][0], a.t, w), v), yv);
+                T0 = cmul(psf_horner(coefS[c][1], a.t, w), v);
+                if (a.npsi > 1) T1 = cmul(psf_horner(coefS[c][2], a.t, w), v);
             }
+            acc[0] += wt * (R.x * R.x + R.y * R.y);
+            acc[1] += wt * (T0.x * R.x + T0.y * R.y);               // Re conj(D0 X^) R
+            if (a.npsi > 1) acc[2] += wt * (T1.x * R.x + T1.y * R.y);
         }
     };
 
@@ -460,7 +488,7 @@ __global__ void k_cols(const ColArgs a) {
         auto sdst = [&](int q, double2 v) {
             if (MODE == COL_FILTER) {
                 const double2 w = __ldg(a.tw + q);
-                const double2 H = psf_horner(coefS[c][0], a.t, w);
+                const double2 H = kern(0, w);
                 const double F = 1.0 / ((H.x * H.x + H.y * H.y) + a.mu);       // filter_FFT, demo:224
                 const double2 X = make_double2(v.x * F, v.y * F);
                 if (kin) {
@@ -474,7 +502,7 @@ __global__ void k_cols(const ColArgs a) {
             }
             const double2 w = __ldg(a.tw + q);
             const int m = (a.opsel == SBD_OP_A || a.opsel == SBD_OP_AT) ? 0 : (a.opsel == SBD_OP_D0 ? 1 : 2);
-            double2 K = psf_horner(coefS[c][m], a.t, w);
+            double2 K = kern(m, w);
             if (a.opsel == SBD_OP_AT) K.y = -K.y;
             const double2 z = cmul(K, v);
             line[fft_pad<N>(q) * C] = make_double2(z.x * a.opscale, z.y * a.opscale);

@@ -105,6 +105,36 @@ __device__ __forceinline__ double2 psf_horner(const double2* __restrict__ a, int
     return acc;
 }
 
+// Point-symmetric 7-tap form (psf_size = 7, the size of every reference demo).  The taps of the three
+// models satisfy h[i][j] = h[6-i][6-j] (also the rotated Gaussian, phi != 0), so the column coefficients
+// c_j(k) = sum_i h[i][j] wk^i obey c_(6-j) = wk^6 conj(c_j).  With d_j = wk^-3 c_j (d_(6-j) = conj d_j) and
+// w = e^(i th), |w| = 1:
+//     sum_j c_j w^j = (wk w)^3 * S,    S = e0 + sum_{m=1..3} (e_m cos(m th) + f_m sin(m th))   REAL
+//     e0 = Re d_3,  e_m = Re(d_(3+m) + d_(3-m)),  f_m = -Im(d_(3+m) - d_(3-m)),  (cos, sin)(m th) = w^m
+// i.e. 6 real multiply-adds per kernel, and the complex factor (wk w)^3 is shared by the three kernels
+// of the likelihood pass (the Horner form costs 24 per kernel).  b[m] = (e_m, f_m); b[0] = (e0, 0).
+struct PsfW3 { double c1, s1, c2, s2; double2 w3; };
+__device__ __forceinline__ PsfW3 psf_w3(double2 w) {
+    const double2 w2 = cmul(w, w);
+    PsfW3 p;
+    p.w3 = cmul(w2, w);
+    p.c1 = w.x; p.s1 = w.y; p.c2 = w2.x; p.s2 = w2.y;
+    return p;
+}
+__device__ __forceinline__ double psf_sym3(const double2* __restrict__ b, const PsfW3& p) {
+    double s = b[0].x;
+    s = fma(b[1].x, p.c1, s); s = fma(b[1].y, p.s1, s);
+    s = fma(b[2].x, p.c2, s); s = fma(b[2].y, p.s2, s);
+    s = fma(b[3].x, p.w3.x, s); s = fma(b[3].y, p.w3.y, s);
+    return s;
+}
+// the (e_m, f_m) pair from the column coefficients c[0..6] and wk3c = conj(wk^3)
+__device__ __forceinline__ double2 psf_sym3_coef(const double2* __restrict__ c, double2 wk3c, int m) {
+    if (m == 0) return make_double2(cmul(wk3c, c[3]).x, 0.0);
+    const double2 hi = cmul(wk3c, c[3 + m]), lo = cmul(wk3c, c[3 - m]);
+    return make_double2(hi.x + lo.x, -(hi.y - lo.y));
+}
+
 // Full rows x cols spectrum for sbd_psf_spectrum (API / parity path only).
 // coef was built with nk = nx.  Output column-major: element (k,q) at q*nx+k.
 __global__ void k_psf_spectrum(int t, int nx, int ny, int m, const double2* __restrict__ coef,

@@ -422,7 +422,7 @@ void rows_inv(sbd_ctx* c, const double2* spec, double* out, int batch) {
 template <int MODE>
 void cols(sbd_ctx* c, const double2* in, double2* out, int batch, int opsel = 0) {
     ColArgs a;
-    a.in = in; a.out = out; a.yhat = c->yhat; a.coef = c->coef; a.tw = c->tw_ny; a.ctl = c->ctl;
+    a.in = in; a.out = out; a.yhat = c->yhat; a.coef = c->coef; a.tw = c->tw_ny; a.tw_x = c->tw_nx; a.ctl = c->ctl;
     a.partials = c->part_col; a.counters = c->cnt_col; a.stats = c->stats;
     a.spec_stride = c->spec_elems; a.nk = c->nk; a.nxfull = c->nx; a.t = c->t;
     a.npsi = (c->model == SBD_LAPLACE) ? 1 : 2; a.C = c->colsKC; a.logC = c->colsLogKC; a.LC = c->colsC;
@@ -542,13 +542,13 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
             c->colsC = C;
             c->colsLogC = (C == 8) ? 3 : (C == 4) ? 2 : (C == 2) ? 1 : 0;
             c->ntiles = (c->nk + C - 1) / C;
-            // columns per block (<= tile width): bounded by threads (<= 1024) and shared memory
+            // columns per block (<= tile width): bounded by threads (<= 512, the launch bound of k_cols) and shared memory
             int KC = C;
             if (const char* e = getenv("SBD_COLS_KC")) {
                 const int v = atoi(e);
                 if ((v == 1 || v == 2 || v == 4 || v == 8) && v <= C) KC = v;
             }
-            while (KC > 1 && ((size_t)KC * cols / 16 > 1024 || (size_t)KC * le_y * 16 > 220 * 1024)) KC /= 2;
+            while (KC > 1 && ((size_t)KC * cols / 16 > 512 || (size_t)KC * le_y * 16 > 220 * 1024)) KC /= 2;
             c->colsKC = KC;
             c->colsLogKC = (KC == 8) ? 3 : (KC == 4) ? 2 : (KC == 2) ? 1 : 0;
             c->cols_smem = (size_t)KC * le_y * 16;

@@ -79,6 +79,34 @@ def test_blur_ops(sbd, O, model, shape):
         assert rel(d_gpu(x, *psi), d(x, *psi)) < TOL
 
 
+@pytest.mark.parametrize("psf_size", [7, 5, 9])
+@pytest.mark.parametrize("phi", [0.3, np.pi / 5])
+def test_blur_ops_rotated_gaussian_and_other_sizes(sbd, O, psf_size, phi):
+    """phi != 0: the Gaussian taps are only point-symmetric; psf_size != 7 takes the Horner path."""
+    shape = (64, 128)
+    rng = np.random.default_rng(psf_size)
+    x = rng.uniform(0, 255, shape)
+    cl_gpu = sbd.host._closures(0, shape, psf_size, phi)
+    cl = O.operators.closures(0, shape, psf_size, phi)
+    psi = PSI[0]
+    assert rel(cl_gpu["A"](x, *psi), cl["A"](x, *psi)) < TOL
+    assert rel(cl_gpu["AT"](x, *psi), cl["AT"](x, *psi)) < TOL
+    for d_gpu, d in zip(cl_gpu["dif"], cl["dif"]):
+        assert rel(d_gpu(x, *psi), d(x, *psi)) < TOL
+    # the fused likelihood pass (residual + both PSF-parameter gradients in one column pass)
+    eng = sbd.engine_for(shape, psf_size, 0, phi)
+    y = cl["A"](x, *psi) + rng.standard_normal(shape)
+    psi2, s2 = (0.5, 0.35), 3.0
+    f, gradF, grads, gsig = O.operators.likelihood_closures(cl, y, x.size)
+    got = eng.likelihood(x, y, psi2, s2, 0.0)
+    args = (*psi2, s2)
+    assert abs(got["f"] - f(x, *args)) <= TOL * abs(f(x, *args))
+    assert rel(got["gradF"], gradF(x, *args)) < TOL
+    for i, gr in enumerate(grads):
+        scale = np.sum(np.abs(cl["dif"][i](x, *psi2) * (cl["A"](x, *psi2) - y))) / s2
+        assert abs(got[f"grad_psi{i}"] - gr(x, *args)) <= TOL * scale
+
+
 @pytest.mark.parametrize("n", [2048, 4096])
 def test_blur_large_properties(sbd, n):
     """Full-size, size-independent properties: A(const)=const, adjointness,
