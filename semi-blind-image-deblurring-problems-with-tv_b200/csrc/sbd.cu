@@ -173,7 +173,7 @@ void set_geometry(sbd_ctx* c, int batch) {
         if (const char* e = getenv("SBD_CHAMB_T")) T = atoi(e);
         if (nx % 2 != 0 || nx < 8) T = 1;           // pairs of pixels must be 16-byte aligned
         if (const char* e = getenv("SBD_CHAMB_PIPE")) c->cm_pipe = atoi(e) != 0;
-        c->cmT = (T == 3 || T == 4 || T == 5) ? T : 1;
+        c->cmT = (T == 3 || T == 4) ? T : 1;
         const int HL = (c->cmT + 1) & ~1, WO = 64 - 2 * HL;
         c->cm_strips = (nx + WO - 1) / WO;
         c->cm_gx = (c->cm_strips + TV_WARPS - 1) / TV_WARPS;
@@ -300,20 +300,18 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
     PhaseTimer* pt = new PhaseTimer(c, 2);
     if (c->cmT > 1) {
         // blocks of fused sweeps; each block = main launch + redo launch (a no-op unless the reference's
-        // stop test fired inside the block).  Block sizes: as many 4-level blocks as possible, with 5-level
-        // blocks absorbing the remainder (K = 25 -> 5,4,4,4,4,4); a short tail runs the generic path.
+        // stop test fired inside the block).  4-level blocks are the most efficient; the block planned
+        // last is an odd one (3 or 1 levels), because odd blocks have a pixel of lateral validity to
+        // spare and can write the prox output themselves (EMIT, tv_multi.cuh): K = 25 -> 4 x6, 1.
         std::vector<int> plan;
         if (c->cmT == 4) {
             const int a = maxiter / 4, r = maxiter % 4;
-            if (a > 0 && r <= a) {
-                for (int i = 0; i < a - r; ++i) plan.push_back(4);
-                for (int i = 0; i < r; ++i) plan.push_back(5);      // a 5-level block last: it can emit f
-            } else {
-                for (int i = 0; i < a; ++i) plan.push_back(4);
-                if (r) plan.push_back(4);           // kernel applies min(4, remaining) levels
-            }
+            if (r == 1 || r == 3) { plan.assign(a, 4); plan.push_back(r); }
+            else if (r == 2) { if (a > 0) { plan.assign(a - 1, 4); plan.push_back(3); plan.push_back(3); } else plan.push_back(3); }
+            else { plan.assign(a - 1, 4); plan.push_back(3); plan.push_back(1); }      // maxiter >= 4 here
         } else {
-            for (int k = 0; k < maxiter; k += c->cmT) plan.push_back(c->cmT);
+            for (int k = 0; k < maxiter; k += c->cmT) plan.push_back(std::min(c->cmT, maxiter - k));
+            if (plan.back() % 2 == 0 && plan.back() > 1) { plan.back() -= 1; plan.push_back(1); }
         }
         for (size_t b = 0; b < plan.size(); ++b) {
             const int T = plan[b];
@@ -321,16 +319,20 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
             const double* pyi = (b & 1) ? c->py1 : c->py0;
             double* pxo = (b & 1) ? c->px0 : c->px1;
             double* pyo = (b & 1) ? c->py0 : c->py1;
-            // the last planned block writes the prox output itself when it has the lateral slack (T = 5)
-            const bool emit = (b + 1 == plan.size()) && T == 5 && c->cm_emit;
-            for (int redo = 0; redo < 2; ++redo) {
-                const int zin = (zero_start && b == 0) ? 1 : 0;
-                if (emit && redo == 0) {
-                    if (keep_duals) chamb_multi_launch<5, false, 2, 1>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin, f);
-                    else chamb_multi_launch<5, false, 2, 2>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin, f);
-                } else if (T == 3) chamb_multi_launch<3, false, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
-                else if (T == 5) chamb_multi_launch<5, false, 2>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
-                else chamb_multi_launch<4, false, 3>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
+            const int zin = (zero_start && b == 0) ? 1 : 0;
+            const bool last = b + 1 == plan.size();
+            const int emit = (last && c->cm_emit && (T & 1)) ? (keep_duals ? 1 : 2) : 0;
+            // a one-level block cannot stop "inside": no redo launch
+            for (int redo = 0; redo < (T > 1 ? 2 : 1); ++redo) {
+                const int em = redo ? 0 : emit;
+#define SBD_CM(T_, MINB_) \
+                if (em == 1) chamb_multi_launch<T_, false, MINB_, 1>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin, f); \
+                else if (em == 2) chamb_multi_launch<T_, false, MINB_, 2>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin, f); \
+                else chamb_multi_launch<T_, false, MINB_, 0>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
+                if (T == 1) { SBD_CM(1, 4) }
+                else if (T == 3) { SBD_CM(3, 3) }
+                else chamb_multi_launch<4, false, 3, 0>(c, g, pxi, pyi, pxo, pyo, batch, redo, zin);
+#undef SBD_CM
                 LAUNCH_CHECK(c);
             }
         }
