@@ -80,12 +80,11 @@ k_tvnorm(const double* __restrict__ x, int nx, int ny, int seg, size_t img_strid
     if (s.warp_on) {
         const int jp = (s.j0 == 0) ? ny - 1 : s.j0 - 1;             // periodic wrap (conv2c.m:27-44)
         const int il = (s.i0 == 0) ? nx - 1 : s.i0 - 1;
-        double prev[V], cur[V];
+        double prev[V];
         ld_row<V>(xi + (size_t)jp * nx + s.i, s.on, prev);
-        for (int j = s.j0; j < s.j1; ++j) {
-            ld_row<V>(xi + (size_t)j * nx + s.i, s.on, cur);
+        auto row = [&](const double (&cur)[V], double left0) {
             double left = shfl_up_d(cur[V - 1], 1);
-            if (s.lane == 0) left = __ldg(xi + (size_t)j * nx + il);
+            if (s.lane == 0) left = left0;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const double dv = cur[v] - (v == 0 ? left : cur[v - 1]);    // diffv: x(i,j)-x(i-1,j)
@@ -93,6 +92,24 @@ k_tvnorm(const double* __restrict__ x, int nx, int ny, int seg, size_t img_strid
                 if (s.i + v < nx) acc[0] += sqrt(dh * dh + dv * dv);
                 prev[v] = cur[v];
             }
+        };
+        // four rows of loads in flight per warp (the sum keeps its row order)
+        constexpr int U = 4;
+        int j = s.j0;
+        for (; j + U <= s.j1; j += U) {
+            double cur[U][V], l0[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                ld_row<V>(xi + (size_t)(j + u) * nx + s.i, s.on, cur[u]);
+                l0[u] = (s.lane == 0) ? __ldg(xi + (size_t)(j + u) * nx + il) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) row(cur[u], l0[u]);
+        }
+        for (; j < s.j1; ++j) {
+            double cur[V];
+            ld_row<V>(xi + (size_t)j * nx + s.i, s.on, cur);
+            row(cur, (s.lane == 0) ? __ldg(xi + (size_t)j * nx + il) : 0.0);
         }
     }
     block_sum<1>(acc, sm);
