@@ -281,19 +281,20 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (fused Chambolle sweeps), live CUDA-event timing.
-    # One prox = `nblk` fused launches (K = 25 -> blocks of 5,4,4,4,4,4 sweeps) + as many no-op redo launches.
     # Algorithmic bytes: 40 B per pixel per SWEEP (read g,px,py; write px,py).
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+    # block plan of sbd.cu chambolle(): K = 25 -> six 4-level launches + a one-level tail launch that also writes
+    # the prox output; phase "chambolle_sweeps" times the 4-level launches (and their no-op redo launches) only
     a4, r4 = CHAMBOLLE_K // 4, CHAMBOLLE_K % 4
-    nblk = a4 if r4 <= a4 else a4 + 1
+    n4 = a4 if r4 in (1, 3) else a4 - 1
     n_prox = int(phases["chambolle_sweeps"][1])
-    launches_timed = n_prox * nblk
+    launches_timed = n_prox * n4
     sweep_ms = phases["chambolle_sweeps"][0] / max(launches_timed, 1)
-    sweep_bytes = 40.0 * npix * nch * CHAMBOLLE_K / nblk       # algorithmic bytes of the sweeps one launch applies
+    sweep_bytes = 40.0 * npix * nch * 4                        # algorithmic bytes of the 4 sweeps one launch applies
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -312,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
                 "note": "one sbd_sapg_run call = K steps; y from pinned host memory in, trajectories + last samples out"},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "k_chamb_multi<T> (T = 4|5 Chambolle sweeps fused per launch)",
+        "roofline": {"bound": "hbm", "kernel": "k_chamb_multi<4> (4 Chambolle sweeps fused per launch)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_ms,
                      "launches_timed": launches_timed, "sweeps_executed_chain0": sweeps_executed,
@@ -321,7 +322,8 @@ def run_ours(args, rank, world, local_rank):
                              "it and the model-based fraction exceeds 1; the kernel is fp64-pipe bound (profiles/)"},
         "fused_step": {"alg_bytes_per_chain_step": alg_bytes_per_chain_step(npix), "achieved_gbs_per_gpu": step_gbs / world,
                        "frac_of_hbm_peak": step_gbs / world / peak,
-                       "phase_ms_per_step": {k_: v_[0] / K for k_, v_ in phases.items()}},
+                       "phase_ms_per_step": {("chambolle_total" if k_ == "chambolle_other" else k_): v_[0] / K
+                                             for k_, v_ in phases.items()}},
         "theta_last": float(th[-1]), "sigma2_last": float(s2[-1]),
     }
     if world == 1 and not args.no_size_sweep:

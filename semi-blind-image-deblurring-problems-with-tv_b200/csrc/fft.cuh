@@ -220,6 +220,7 @@ __device__ __forceinline__ size_t spec_idx(const SpecGeom& g, int k, int q) {
 // The passes hold one to three blocks per SM and a block's first stage waits for
 // all its data (DRAM ~2000 cycles under load here), so the block that takes over
 // the SM one wave later should find its input in L2.  pf = resident blocks.
+// Measured at 4096^2 x 8: likelihood column pass 1.22 -> 1.10 ms, forward rows pass 0.58 -> 0.55 ms.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void l2_prefetch(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -271,29 +272,17 @@ __global__ void k_rows_fwd(const double* __restrict__ x, double2* __restrict__ s
 
 // rows pass, inverse: half spectra -> real lines (unnormalised; the 1/(nx*ny)
 // factor is folded into the spectral multiply of the column pass)
+// (no prefetch here: its registers cost this pass the third resident block, 0.87 -> 0.68 ms at 4096^2 x 8)
 template <int N>
-__global__ void k_rows_inv(const double2* __restrict__ spec, double* __restrict__ out, SpecGeom sg, int LP,
-                           size_t img_stride, size_t spec_stride, const double2* __restrict__ tw, int pf) {
+__global__ void __launch_bounds__(256, 3)
+k_rows_inv(const double2* __restrict__ spec, double* __restrict__ out, SpecGeom sg, int LP,
+           size_t img_stride, size_t spec_stride, const double2* __restrict__ tw) {
     extern __shared__ double2 fsm[];
     constexpr int TL = N / 16, LE = fft_line_elems<N>();
     const int img = blockIdx.y;
     const int line0 = 2 * blockIdx.x * LP;
     const double2* si = spec + (size_t)img * spec_stride;
     constexpr int HB = N / 2 + 1;
-    {
-        // the 2*LP lines of a block are one contiguous piece of 2*LP*C bins in every tile
-        const unsigned int nxt = blockIdx.y * gridDim.x + blockIdx.x + pf;
-        if (pf > 0 && nxt < gridDim.x * gridDim.y) {
-            const unsigned int i2 = nxt / gridDim.x, b2 = nxt - i2 * gridDim.x;
-            const double2* s2 = spec + (size_t)i2 * spec_stride;
-            const int piece = 2 * LP * sg.C * (int)sizeof(double2);
-            const int lpp = (piece + 127) / 128, ntile = (HB + sg.C - 1) >> sg.logC;
-            for (int e = threadIdx.x; e < ntile * lpp; e += blockDim.x) {
-                const int kt = e / lpp, l = e - kt * lpp;
-                l2_prefetch(reinterpret_cast<const char*>(s2 + spec_idx(sg, kt << sg.logC, 2 * b2 * LP)) + l * 128);
-            }
-        }
-    }
     for (int e = threadIdx.x; e < LP * HB; e += blockDim.x) {
         const int bb = e / HB, k = e - bb * HB;
         double2* L = fsm + (size_t)bb * LE;

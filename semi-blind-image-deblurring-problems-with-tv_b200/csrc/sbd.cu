@@ -315,6 +315,7 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
         }
         for (size_t b = 0; b < plan.size(); ++b) {
             const int T = plan[b];
+            if (pt && T != 4) { delete pt; pt = nullptr; }      // phase 2 = the 4-level launches only
             const double* pxi = (b & 1) ? c->px1 : c->px0;
             const double* pyi = (b & 1) ? c->py1 : c->py0;
             double* pxo = (b & 1) ? c->px0 : c->px1;
@@ -350,7 +351,7 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
             LAUNCH_CHECK(c);
         }
     }
-    delete pt;
+    if (pt) delete pt;
     if (c->tvV == 2)
         k_chamb_out<2><<<grid, TV_THREADS, 0, c->stream>>>(g, c->px0, c->py0, c->px1, c->py1, f, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst);
     else
@@ -412,8 +413,7 @@ void rows_inv(sbd_ctx* c, const double2* spec, double* out, int batch) {
     const SpecGeom sg = spec_geom(c);
     switch (c->nx) {
 #define X(N) case N: set_smem(k_rows_inv<N>, smem); \
-        k_rows_inv<N><<<g, c->rowsT, smem, c->stream>>>(spec, out, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx, \
-                                                        resident_blocks(c, k_rows_inv<N>, c->rowsT, smem)); break;
+        k_rows_inv<N><<<g, c->rowsT, smem, c->stream>>>(spec, out, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
         SBD_FFT_SIZES(X)
 #undef X
         default: throw Error{SBD_E_UNSUPPORTED, "rows_inv: unsupported size"};
