@@ -59,6 +59,51 @@ __device__ __forceinline__ void fast_sqrt_rcp(double a, double tau, double& tmp,
 struct CmPk { double px[2], py[2], g[2]; };             // a row travelling up the levels
 struct CmLv { double px[2], py[2], u[2], g[2]; };       // the row a level holds
 
+// sqrt seed of a >= 0 with a == 0 mapped to a tiny normal (a * y is then exactly 0): MUFU.RSQ64H only
+// reads the high word, so the clamp is one integer instruction instead of an fp64 add
+__device__ __forceinline__ double fast_rsqrt_seed_nz(double a) {
+    const int hi = max(__double2hiint(a), 0x00100000);
+    return fast_rsqrt_seed(__hiloint2double(hi, __double2loint(a)));
+}
+
+// The arithmetic of one level step for the two pixels of a lane, given upx (:162-163) and the new u
+// (:159).  Written stage by stage (all of stage k for both pixels before stage k+1): ptxas keeps roughly
+// this order, and back-to-back dependent fp64 instructions of ONE chain each wait out the pipe latency.
+// On B200 an fp64 instruction holds the SMSP's issue port for two cycles and every other instruction
+// for one (tools/fp64_microbench.cu, MIX lines), so the kernel is issue-bound and every instruction
+// counts: the square root / reciprocal refinement is written with the fewest operations that reach
+// ~1 ulp (see fast_sqrt_rcp for the derivation; here r' = 1 - g*y = 2r saves the 0.5*y product).
+template <class Lv>
+__device__ __forceinline__ void cm_core(const double (&upx)[2], const double (&un)[2], const Lv& h, double tau,
+                                        double (&opx)[2], double (&opy)[2], double (&ex)[2]) {
+    double upy[2], s2[2], y[2], g[2], rs[2], r[2], t[2], d[2], ee[2], ey[2];
+#define CM_V _Pragma("unroll") for (int v = 0; v < 2; ++v)
+    CM_V upy[v] = un[v] - h.u[v];
+    CM_V s2[v] = upy[v] * upy[v];
+    CM_V s2[v] = fma(upx[v], upx[v], s2[v]);
+    CM_V y[v] = fast_rsqrt_seed_nz(s2[v]);
+    CM_V g[v] = s2[v] * y[v];
+    CM_V rs[v] = fast_rcp_seed(fma(tau, g[v], 1.0));
+    CM_V r[v] = fma(-g[v], y[v], 1.0);                                       // 2r of fast_sqrt_rcp
+    CM_V t[v] = fma(r[v], 0.375, 0.5);
+    CM_V t[v] = r[v] * t[v];                                                 // r + 1.5 r^2
+    CM_V g[v] = fma(g[v], t[v], g[v]);                                       // :127
+    CM_V d[v] = fma(tau, g[v], 1.0);
+    CM_V ex[v] = fma(g[v], h.px[v], -upx[v]);
+    CM_V ey[v] = fma(g[v], h.py[v], -upy[v]);
+    CM_V ee[v] = fma(-d[v], rs[v], 1.0);
+    CM_V ey[v] = ey[v] * ey[v];
+    CM_V opx[v] = fma(tau, upx[v], h.px[v]);
+    CM_V opy[v] = fma(tau, upy[v], h.py[v]);
+    CM_V ee[v] = fma(ee[v], ee[v], ee[v]);
+    CM_V ex[v] = fma(ex[v], ex[v], ey[v]);                                   // :128
+    CM_V rs[v] = fma(rs[v], ee[v], rs[v]);
+    CM_V opx[v] = opx[v] * rs[v];                                            // :129
+    CM_V opy[v] = opy[v] * rs[v];                                            // :130
+#undef CM_V
+}
+
+
 struct CmLane {         // lane constants
     int i;              // fast-axis index of this lane's first pixel
     bool in0, in1;      // pixel inside the image
@@ -93,20 +138,12 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
         if (L.last0) upx[0] = 0.0;
         if (L.last1) upx[1] = 0.0;
     }
-    double e = 0.0;
     CmPk o;
+    double ex[2];
+    cm_core(upx, un, h, tau, o.px, o.py, ex);
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
-        const double upy = un[v] - h.u[v];
-        const double s2 = fma(upx[v], upx[v], upy * upy);
-        double tmp, rinv;
-        fast_sqrt_rcp(s2, tau, tmp, rinv);                                   // :127 and 1/(1 + tau*tmp)
-        const double ex = fma(tmp, h.px[v], -upx[v]), ey = fma(tmp, h.py[v], -upy);
-        e += fma(ex, ex, ey * ey);                                           // :128
-        o.px[v] = fma(tau, upx[v], h.px[v]) * rinv;                          // :129
-        o.py[v] = fma(tau, upy, h.py[v]) * rinv;                             // :130
-        o.g[v] = h.g[v];
-    }
+    for (int v = 0; v < 2; ++v) o.g[v] = h.g[v];
+    const double e = ex[0] + ex[1];
     if (EDGE) {
         if (!L.in0) { o.px[0] = 0.0; o.py[0] = 0.0; }
         if (!L.in1) { o.px[1] = 0.0; o.py[1] = 0.0; }
@@ -116,6 +153,38 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
 #pragma unroll
     for (int v = 0; v < 2; ++v) { h.px[v] = p.px[v]; h.py[v] = p.py[v]; h.u[v] = un[v]; h.g[v] = p.g[v]; }
     p = o;
+}
+
+// Fast-path level step without register rotation (interior rows, all levels live).  `ho` is the
+// level's old state; `hn` its new state, whose px, py, g were already written by the level below (or by
+// the load) and whose u is formed here; the row the level emits goes straight into the new state of
+// the level above (`up`).  A trip of two rows alternates two state sets, so no value is ever copied
+// (the rotating form spent one instruction in six on register moves).  err is not masked here.
+template <bool EDGE>
+__device__ __forceinline__ void cm_step2(const CmLv& ho, CmLv& hn, CmLv& up, const CmLane& L, double tau, double& err) {
+    const double pxl = shfl_up_d(hn.px[1], 1);
+    double ux0 = hn.px[0] - pxl, ux1 = hn.px[1] - hn.px[0];                 // :156-157
+    if (EDGE) {
+        if (L.last0) ux0 = -hn.px[0];
+        if (L.last1) ux1 = -hn.px[1];
+    }
+    const double uy0 = hn.py[0] - ho.py[0], uy1 = hn.py[1] - ho.py[1];     // :153-154
+    hn.u[0] = (uy0 + ux0) - hn.g[0];                                        // :159, :124
+    hn.u[1] = (uy1 + ux1) - hn.g[1];
+    const double ur = shfl_down_d(ho.u[0], 1);
+    double upx[2] = {ho.u[1] - ho.u[0], ur - ho.u[1]};                      // :162-163
+    if (EDGE) {
+        if (L.last0) upx[0] = 0.0;
+        if (L.last1) upx[1] = 0.0;
+    }
+    double ex[2];
+    cm_core(upx, hn.u, ho, tau, up.px, up.py, ex);
+    up.g[0] = ho.g[0]; up.g[1] = ho.g[1];
+    if (EDGE) {
+        if (!L.in0) { up.px[0] = 0.0; up.py[0] = 0.0; }
+        if (!L.in1) { up.px[1] = 0.0; up.py[1] = 0.0; }
+    }
+    err += ex[0] + ex[1];
 }
 
 // ZERO: the incoming dual pair is identically zero (chambolle_prox_TV_stop.m:68-69) and is not loaded
@@ -285,36 +354,47 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
         const int fast_lo = j0 + D * (T - 1) + 1, fast_hi = min(j1, ny - 2);
         for (; r < min(fast_lo, rend + 1); ++r)
             cm_generic_iter<T, EDGE, PIPE, ZERO, EMIT>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev, f, lambda, prevpy);
-        // Two rows per trip with two named prefetch buffers: the row loaded during one half is
-        // first touched in the next half, a full level-sweep later, and no register rotation
-        // (which the compiler would schedule right behind the load) is needed.
-        auto fast_body = [&](const CmPk& cur, int rr) {
-            CmPk loc[T];
-            cm_take(CM_BOX(0), cur, invlam);
+        // Two rows per trip.  Two named prefetch buffers: the row loaded during one half is first
+        // touched in the next half, a full level-sweep later.  Two level-state sets: the first row of a
+        // trip reads `h` and builds `hb`, the second reads `hb` and rebuilds `h` (cm_step2), so the
+        // loop carries no register rotation at all.
+        auto fast_row = [&](const CmPk& cur, int rr, const CmLv (&ho)[T], CmLv (&hn)[T]) {
 #pragma unroll
-            for (int q = 0; q < T; ++q) {
-                const int s = PIPE ? T - 1 - q : q;
-                CmPk p = CM_BOX(s);
-                cm_step<EDGE, false>(h[s], p, L, tau, err[s], false, false, true);
-                if (s == T - 1) {
-                    const size_t o = (size_t)((long long)(rr - D * (T - 1) - 1) * nx + ibase);
-                    if (EMIT) cm_emit<EDGE, EMIT>(p, prevpy, f, pxo, pyo, o, L, lambda, true, false);
-                    else cm_store<EDGE>(p, pxo, pyo, o, L);
-                } else CM_BOX(s + 1) = p;
+            for (int v = 0; v < 2; ++v) { hn[0].px[v] = cur.px[v]; hn[0].py[v] = cur.py[v]; hn[0].g[v] = cur.g[v] * invlam; }   // g / lambda (:124)
+            CmLv top;
+#pragma unroll
+            for (int s = 0; s < T; ++s) {
+                if (s + 1 < T) cm_step2<EDGE>(ho[s], hn[s], hn[s + 1], L, tau, err[s]);
+                else cm_step2<EDGE>(ho[s], hn[s], top, L, tau, err[s]);
             }
+            CmPk p;
+#pragma unroll
+            for (int v = 0; v < 2; ++v) { p.px[v] = top.px[v]; p.py[v] = top.py[v]; p.g[v] = top.g[v]; }
+            const size_t o = (size_t)((long long)(rr - (T - 1) - 1) * nx + ibase);
+            if (EMIT) cm_emit<EDGE, EMIT>(p, prevpy, f, pxo, pyo, o, L, lambda, true, false);
+            else cm_store<EDGE>(p, pxo, pyo, o, L);
         };
-        if (r <= fast_hi) {
+        if (!PIPE && r <= fast_hi) {
             CmPk nA = nxt, nB;
-            while (r + 1 <= fast_hi) {
-                cm_prefetch<EDGE, ZERO>(g, pxi, pyi, (size_t)((long long)min(r + 1 + CM_PF, ny - 1) * nx + ibase), L);
-                cm_load<EDGE, ZERO>(nB, g, pxi, pyi, (size_t)((long long)(r + 1) * nx + ibase), L);
-                fast_body(nA, r);
-                cm_prefetch<EDGE, ZERO>(g, pxi, pyi, (size_t)((long long)min(r + 2 + CM_PF, ny - 1) * nx + ibase), L);
-                cm_load<EDGE, ZERO>(nA, g, pxi, pyi, (size_t)((long long)(r + 2) * nx + ibase), L);
-                fast_body(nB, r + 1);
-                r += 2;
-            }
+            CmLv hb[T];
+            auto trip = [&](int rr) {
+                cm_prefetch<EDGE, ZERO>(g, pxi, pyi, (size_t)((long long)min(rr + 1 + CM_PF, ny - 1) * nx + ibase), L);
+                cm_load<EDGE, ZERO>(nB, g, pxi, pyi, (size_t)((long long)(rr + 1) * nx + ibase), L);
+                fast_row(nA, rr, h, hb);
+                cm_prefetch<EDGE, ZERO>(g, pxi, pyi, (size_t)((long long)min(rr + 2 + CM_PF, ny - 1) * nx + ibase), L);
+                cm_load<EDGE, ZERO>(nA, g, pxi, pyi, (size_t)((long long)(rr + 2) * nx + ibase), L);
+                fast_row(nB, rr + 1, hb, h);
+            };
+            // (four rows per trip would halve the ~60 register moves ptxas leaves at the back edge, but the
+            // loop then outgrows the instruction cache close to the SMSP: ncu shows no_instruction stalls
+            // and no net gain)
+            for (; r + 1 <= fast_hi; r += 2) trip(r);
             nxt = nA;                               // row r, for the generic iterations that follow
+            // the fast rows add their err terms unmasked: lanes outside the output region hold 0
+            if (!L.central) {
+#pragma unroll
+                for (int s = 0; s < T; ++s) err[s] = 0.0;
+            }
         }
     }
     for (; r <= rend; ++r)
