@@ -300,7 +300,7 @@ def run_ours(args, rank, world, local_rank):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp) and n == 4096 and nch == 8:
         try:
-            traffic = json.load(open(tp)).get("k_chamb_multi<4, 0, 3, 0>")
+            traffic = json.load(open(tp)).get("k_chamb_multi<4, 0, 3, 0, 0>")
         except Exception:
             traffic = None
     step_gbs = alg_bytes_per_chain_step(npix) * value / 1e9
