@@ -13,6 +13,7 @@
 
 #include <dlfcn.h>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <limits>
 #include <map>
@@ -92,6 +93,7 @@ struct sbd_ctx {
     unsigned int *cnt_tv = nullptr, *cnt_col = nullptr, *cnt_sq = nullptr;
     double *stats = nullptr, *allstats = nullptr;
     double *part_tv = nullptr, *part_ch = nullptr, *part_col = nullptr, *part_sq = nullptr;
+    double *in_y = nullptr, *in_x0 = nullptr, *in_xt = nullptr;         // staging images of the host-pointer entries
     double* psi_dev = nullptr;      // [2] override for operator calls
     // workspaces (sized for ws_batch images)
     int ws_batch = 0;
@@ -591,6 +593,7 @@ int sbd_destroy(sbd_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     free_ws(c);
+    dfree(c->in_y); dfree(c->in_x0); dfree(c->in_xt);
     dfree(c->tw_nx); dfree(c->tw_ny); dfree(c->taps); dfree(c->coef); dfree(c->ctl); dfree(c->psi_dev);
     dfree(c->ximg); dfree(c->yhat); dfree(c->allstats); dfree(c->post);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1224,6 +1227,11 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     c->profile = false;
 
     // ---- err_psf on the device, then bring the trajectories home
+    const bool dbg_host = getenv("SBD_TRACE_HOST") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double H0 = now_ms();
+    if (dbg_host) { cudaStreamSynchronize(s); fprintf(stderr, "[sbd] impl: loops drained after %.1f ms more\n", now_ms() - H0); }
+    const double H1 = now_ms();
     double* d_errpsf = dt.mk<double>(samples, s);
     k_err_psf<<<samples, 256, 0, s>>>(c->model, c->t, c->phi, dt.t.psi0, dt.t.psi1, prm->err_psf_lag,
                                       prm->psi_true[0], prm->psi_true[1], samples, d_errpsf);
@@ -1253,6 +1261,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
         SBD_CUDA(cudaMemcpyAsync(out->X_mean, c->Gf, sizeof(double) * c->npix, cudaMemcpyDeviceToHost, s));
     }
     SBD_CUDA(cudaStreamSynchronize(s));
+    if (dbg_host) fprintf(stderr, "[sbd] impl: read-back %.1f ms\n", now_ms() - H1);
     float ms = 0.f;
     SBD_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     out->seconds = ms * 1e-3;
@@ -1310,28 +1319,46 @@ int sbd_sapg_run_dev(sbd_ctx* c, const double* d_y, const double* d_X0, const sb
 int sbd_sapg_run(sbd_ctx* c, const double* y, const double* X0, const double* x_true,
                  const sbd_params* prm, const double* noise, sbd_traces* out) {
     if (!c) return SBD_E_INVALID;
-    double *d_y = nullptr, *d_x0 = nullptr, *d_xt = nullptr, *d_nz = nullptr;
+    double *d_x0 = nullptr, *d_xt = nullptr, *d_nz = nullptr;
     int rc = SBD_OK;
+    const bool dbg = getenv("SBD_TRACE_HOST") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double T0 = now();
+    double T1 = T0, T2 = T0;
     try {
         SBD_REQUIRE(y && prm && out, SBD_E_INVALID, "sbd_sapg_run: y/params/traces NULL");
         SBD_CUDA(cudaSetDevice(c->device));
         const size_t bytes = sizeof(double) * c->npix;
-        d_y = dalloc<double>(c->npix);
-        SBD_CUDA(cudaMemcpyAsync(d_y, y, bytes, cudaMemcpyHostToDevice, c->stream));
-        if (X0) { d_x0 = dalloc<double>(c->npix); SBD_CUDA(cudaMemcpyAsync(d_x0, X0, bytes, cudaMemcpyHostToDevice, c->stream)); }
-        if (x_true) { d_xt = dalloc<double>(c->npix); SBD_CUDA(cudaMemcpyAsync(d_xt, x_true, bytes, cudaMemcpyHostToDevice, c->stream)); }
+        // staging images live in the context: a cudaFree per call was measured to cost up to 0.6 s here
+        // (it tears down whatever the driver deferred, e.g. the graphs of the run)
+        if (!c->in_y) c->in_y = dalloc<double>(c->npix);
+        SBD_CUDA(cudaMemcpyAsync(c->in_y, y, bytes, cudaMemcpyHostToDevice, c->stream));
+        if (X0) {
+            if (!c->in_x0) c->in_x0 = dalloc<double>(c->npix);
+            d_x0 = c->in_x0;
+            SBD_CUDA(cudaMemcpyAsync(d_x0, X0, bytes, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (x_true) {
+            if (!c->in_xt) c->in_xt = dalloc<double>(c->npix);
+            d_xt = c->in_xt;
+            SBD_CUDA(cudaMemcpyAsync(d_xt, x_true, bytes, cudaMemcpyHostToDevice, c->stream));
+        }
         if (noise) {
             const size_t draws = (size_t)std::max(prm->warmup - 1, 0) + (size_t)std::max(prm->samples - 1, 0);
             const size_t n = draws * (size_t)prm->n_chains * c->npix;
             d_nz = dalloc<double>(n);
             SBD_CUDA(cudaMemcpyAsync(d_nz, noise, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
         }
-        sapg_run_impl(c, d_y, d_x0, d_xt, prm, d_nz, out);
+        T1 = now();
+        sapg_run_impl(c, c->in_y, d_x0, d_xt, prm, d_nz, out);
+        T2 = now();
     } catch (const Error& e) {
         rc = fail(c, e);
     }
     cudaStreamSynchronize(c->stream);
-    cudaFree(d_y); cudaFree(d_x0); cudaFree(d_xt); cudaFree(d_nz);
+    const double T3 = now();
+    if (d_nz) cudaFree(d_nz);
+    if (dbg) fprintf(stderr, "[sbd] sapg_run host ms: inputs %.1f  impl %.1f  sync %.1f  free %.1f\n", T1 - T0, T2 - T1, T3 - T2, now() - T3);
     return rc;
 }
 
