@@ -75,28 +75,26 @@ __device__ __forceinline__ double fast_rsqrt_seed_nz(double a) {
 // ~1 ulp (see fast_sqrt_rcp for the derivation; here r' = 1 - g*y = 2r saves the 0.5*y product).
 template <class Lv>
 __device__ __forceinline__ void cm_core(const double (&upx)[2], const double (&un)[2], const Lv& h, double tau,
-                                        double (&opx)[2], double (&opy)[2], double (&ex)[2]) {
-    double upy[2], s2[2], y[2], g[2], rs[2], r[2], t[2], d[2], ee[2], ey[2];
+                                        double (&opx)[2], double (&opy)[2], double (&ex)[2], double (&ey)[2]) {
+    double upy[2], s2[2], y[2], g[2], rs[2], r[2], t[2], d[2], ee[2];
 #define CM_V _Pragma("unroll") for (int v = 0; v < 2; ++v)
     CM_V upy[v] = un[v] - h.u[v];
     CM_V s2[v] = upy[v] * upy[v];
     CM_V s2[v] = fma(upx[v], upx[v], s2[v]);
     CM_V y[v] = fast_rsqrt_seed_nz(s2[v]);
     CM_V g[v] = s2[v] * y[v];
-    CM_V rs[v] = fast_rcp_seed(fma(tau, g[v], 1.0));
     CM_V r[v] = fma(-g[v], y[v], 1.0);                                       // 2r of fast_sqrt_rcp
     CM_V t[v] = fma(r[v], 0.375, 0.5);
     CM_V t[v] = r[v] * t[v];                                                 // r + 1.5 r^2
     CM_V g[v] = fma(g[v], t[v], g[v]);                                       // :127
     CM_V d[v] = fma(tau, g[v], 1.0);
+    CM_V rs[v] = fast_rcp_seed(d[v]);                                        // seed from the final d: no early estimate to compute
     CM_V ex[v] = fma(g[v], h.px[v], -upx[v]);
     CM_V ey[v] = fma(g[v], h.py[v], -upy[v]);
     CM_V ee[v] = fma(-d[v], rs[v], 1.0);
-    CM_V ey[v] = ey[v] * ey[v];
     CM_V opx[v] = fma(tau, upx[v], h.px[v]);
     CM_V opy[v] = fma(tau, upy[v], h.py[v]);
     CM_V ee[v] = fma(ee[v], ee[v], ee[v]);
-    CM_V ex[v] = fma(ex[v], ex[v], ey[v]);                                   // :128
     CM_V rs[v] = fma(rs[v], ee[v], rs[v]);
     CM_V opx[v] = opx[v] * rs[v];                                            // :129
     CM_V opy[v] = opy[v] * rs[v];                                            // :130
@@ -139,11 +137,11 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
         if (L.last1) upx[1] = 0.0;
     }
     CmPk o;
-    double ex[2];
-    cm_core(upx, un, h, tau, o.px, o.py, ex);
+    double ex[2], ey[2];
+    cm_core(upx, un, h, tau, o.px, o.py, ex, ey);
 #pragma unroll
     for (int v = 0; v < 2; ++v) o.g[v] = h.g[v];
-    const double e = ex[0] + ex[1];
+    const double e = fma(ex[1], ex[1], fma(ey[1], ey[1], fma(ex[0], ex[0], ey[0] * ey[0])));      // :128
     if (EDGE) {
         if (!L.in0) { o.px[0] = 0.0; o.py[0] = 0.0; }
         if (!L.in1) { o.px[1] = 0.0; o.py[1] = 0.0; }
@@ -177,14 +175,15 @@ __device__ __forceinline__ void cm_step2(const CmLv& ho, CmLv& hn, CmLv& up, con
         if (L.last0) upx[0] = 0.0;
         if (L.last1) upx[1] = 0.0;
     }
-    double ex[2];
-    cm_core(upx, hn.u, ho, tau, up.px, up.py, ex);
+    double ex[2], ey[2];
+    cm_core(upx, hn.u, ho, tau, up.px, up.py, ex, ey);
     up.g[0] = ho.g[0]; up.g[1] = ho.g[1];
     if (EDGE) {
         if (!L.in0) { up.px[0] = 0.0; up.py[0] = 0.0; }
         if (!L.in1) { up.px[1] = 0.0; up.py[1] = 0.0; }
     }
-    err += ex[0] + ex[1];
+    // :128, the four squares go straight into the level's accumulator (one fp64 op per square)
+    err = fma(ex[1], ex[1], fma(ey[1], ey[1], fma(ex[0], ex[0], fma(ey[0], ey[0], err))));
 }
 
 // ZERO: the incoming dual pair is identically zero (chambolle_prox_TV_stop.m:68-69) and is not loaded
