@@ -37,24 +37,11 @@ __device__ __forceinline__ double fast_rcp_seed(double a) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     return y;
 }
-// tmp = sqrt(a) (a >= 0; a == 0 -> exactly 0) and rinv = 1/(1 + tau*tmp), ~1 ulp each.
-// MUFU seeds + Goldschmidt / Newton steps; the reciprocal seed is taken from the
-// first (2^-20) sqrt estimate so that its MUFU latency overlaps the refinement.
-__device__ __forceinline__ void fast_sqrt_rcp(double a, double tau, double& tmp, double& rinv) {
-    const double y = fast_rsqrt_seed(a + 1e-300);
-    double g = a * y;
-    const double h = 0.5 * y;
-    double rs = fast_rcp_seed(fma(tau, g, 1.0));
-    // third-order steps: same dependency depth as two second-order ones, two fp64 ops fewer.
-    // y = (1+dl)/sqrt(a)  =>  r = 0.5 - g*h = -(dl + dl^2/2),  1/(1+dl) = 1 + r + 1.5 r^2 + O(r^3)
-    const double r = fma(-g, h, 0.5);
-    const double t = r * fma(r, 1.5, 1.0);
-    g = fma(g, t, g);                               // |rel err| ~ 2.5 |r|^3 < 2^-60
-    const double d = fma(tau, g, 1.0);
-    const double e = fma(-d, rs, 1.0);              // the seed is 1/d to ~2^-19 (seed error + d known to 2^-20)
-    rs = fma(rs, fma(e, e, e), rs);                 // 1/d = rs (1 + e + e^2 + O(e^3)): ~2^-57
-    tmp = g; rinv = rs;
-}
+// sqrt and reciprocal of a level step (cm_core), ~1 ulp each, from MUFU seeds and one third-order step:
+//   y = (1+dl)/sqrt(a) (seed), g0 = a*y, r = 1 - g0*y = -(2 dl + dl^2), 1/(1+dl) = 1 + r/2 + 3/8 r^2 + O(r^3)
+//     => sqrt(a) = g0 + g0*(r*(0.5 + 0.375 r)),   |rel err| ~ 0.3 |r|^3 < 2^-60   (a == 0 -> exactly 0)
+//   d = 1 + tau*sqrt(a), rs = seed(1/d), e = 1 - d*rs  =>  1/d = rs + rs*(e + e^2) + O(e^3)
+// (an IEEE sqrt plus an IEEE division cost ~3x the fp64 instructions)
 
 struct CmPk { double px[2], py[2], g[2]; };             // a row travelling up the levels
 struct CmLv { double px[2], py[2], u[2], g[2]; };       // the row a level holds
@@ -65,6 +52,12 @@ __device__ __forceinline__ double fast_rsqrt_seed_nz(double a) {
     const int hi = max(__double2hiint(a), 0x00100000);
     return fast_rsqrt_seed(__hiloint2double(hi, __double2loint(a)));
 }
+// The MUFU seeds only define the high word (the PTX instruction zeroes the low one with an extra move).
+// A seed does not care about its low word, so it is taken from a value that is dead anyway; ptxas can
+// then write the MUFU result next to it and drop the move.
+__device__ __forceinline__ double seed_with_low_of(double seed, double dead) {
+    return __hiloint2double(__double2hiint(seed), __double2loint(dead));
+}
 
 // The arithmetic of one level step for the two pixels of a lane, given upx (:162-163) and the new u
 // (:159).  Written stage by stage (all of stage k for both pixels before stage k+1): ptxas keeps roughly
@@ -72,23 +65,24 @@ __device__ __forceinline__ double fast_rsqrt_seed_nz(double a) {
 // On B200 an fp64 instruction holds the SMSP's issue port for two cycles and every other instruction
 // for one (tools/fp64_microbench.cu, MIX lines), so the kernel is issue-bound and every instruction
 // counts: the square root / reciprocal refinement is written with the fewest operations that reach
-// ~1 ulp (see fast_sqrt_rcp for the derivation; here r' = 1 - g*y = 2r saves the 0.5*y product).
+// ~1 ulp (derivation above).
 template <class Lv>
 __device__ __forceinline__ void cm_core(const double (&upx)[2], const double (&un)[2], const Lv& h, double tau,
                                         double (&opx)[2], double (&opy)[2], double (&ex)[2], double (&ey)[2]) {
     double upy[2], s2[2], y[2], g[2], rs[2], r[2], t[2], d[2], ee[2];
 #define CM_V _Pragma("unroll") for (int v = 0; v < 2; ++v)
     CM_V upy[v] = un[v] - h.u[v];
-    CM_V s2[v] = upy[v] * upy[v];
-    CM_V s2[v] = fma(upx[v], upx[v], s2[v]);
-    CM_V y[v] = fast_rsqrt_seed_nz(s2[v]);
+    double sq[2];
+    CM_V sq[v] = upy[v] * upy[v];
+    CM_V s2[v] = fma(upx[v], upx[v], sq[v]);
+    CM_V y[v] = seed_with_low_of(fast_rsqrt_seed_nz(s2[v]), sq[v]);
     CM_V g[v] = s2[v] * y[v];
-    CM_V r[v] = fma(-g[v], y[v], 1.0);                                       // 2r of fast_sqrt_rcp
+    CM_V r[v] = fma(-g[v], y[v], 1.0);
     CM_V t[v] = fma(r[v], 0.375, 0.5);
     CM_V t[v] = r[v] * t[v];                                                 // r + 1.5 r^2
     CM_V g[v] = fma(g[v], t[v], g[v]);                                       // :127
     CM_V d[v] = fma(tau, g[v], 1.0);
-    CM_V rs[v] = fast_rcp_seed(d[v]);                                        // seed from the final d: no early estimate to compute
+    CM_V rs[v] = seed_with_low_of(fast_rcp_seed(d[v]), t[v]);                                        // seed from the final d: no early estimate to compute
     CM_V ex[v] = fma(g[v], h.px[v], -upx[v]);
     CM_V ey[v] = fma(g[v], h.py[v], -upy[v]);
     CM_V ee[v] = fma(-d[v], rs[v], 1.0);
