@@ -347,42 +347,51 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
         const int fast_lo = j0 + D * (T - 1) + 1, fast_hi = min(j1, ny - 2);
         for (; r < min(fast_lo, rend + 1); ++r)
             cm_generic_iter<T, EDGE, PIPE, ZERO, EMIT>(r, h, inbox, nxt, err, g, pxi, pyi, pxo, pyo, nx, ny, j0, jlast, r0, ibase, L, invlam, tau, nlev, f, lambda, prevpy);
-        // Two rows per trip.  Two named prefetch buffers: the row loaded during one half is first
-        // touched in the next half, a full level-sweep later.  Two level-state sets: the first row of a
-        // trip reads `h` and builds `hb`, the second reads `hb` and rebuilds `h` (cm_step2), so the
-        // loop carries no register rotation at all.
-        auto fast_row = [&](const CmPk& cur, int rr, const CmLv (&ho)[T], CmLv (&hn)[T]) {
-#pragma unroll
-            for (int v = 0; v < 2; ++v) { hn[0].px[v] = cur.px[v]; hn[0].py[v] = cur.py[v]; hn[0].g[v] = cur.g[v] * invlam; }   // g / lambda (:124)
-            CmLv top;
-#pragma unroll
-            for (int s = 0; s < T; ++s) {
-                if (s + 1 < T) cm_step2<EDGE>(ho[s], hn[s], hn[s + 1], L, tau, err[s]);
-                else cm_step2<EDGE>(ho[s], hn[s], top, L, tau, err[s]);
-            }
-            CmPk p;
-#pragma unroll
-            for (int v = 0; v < 2; ++v) { p.px[v] = top.px[v]; p.py[v] = top.py[v]; p.g[v] = top.g[v]; }
-            const size_t o = (size_t)((long long)(rr - (T - 1) - 1) * nx + ibase);
-            if (EMIT) cm_emit<EDGE, EMIT>(p, prevpy, f, pxo, pyo, o, L, lambda, true, false);
-            else cm_store<EDGE>(p, pxo, pyo, o, L);
-        };
+        // Two rows per trip over two level-state sets: the first row of a trip reads `h` and builds `hb`,
+        // the second reads `hb` and rebuilds `h` (cm_step2), so the loop carries no register rotation.
+        // The next row is loaded straight into the level-0 state that has just been consumed (three
+        // quarters of a row ahead of its use; the L2 prefetch runs CM_PF rows ahead of that), and the
+        // load / prefetch / store addresses are running pointers.
         if (!PIPE && r <= fast_hi) {
-            CmPk nA = nxt, nB;
             CmLv hb[T];
-            auto trip = [&](int rr) {
-                cm_prefetch<EDGE, ZERO>(g, pxi, pyi, (size_t)((long long)min(rr + 1 + CM_PF, ny - 1) * nx + ibase), L);
-                cm_load<EDGE, ZERO>(nB, g, pxi, pyi, (size_t)((long long)(rr + 1) * nx + ibase), L);
-                fast_row(nA, rr, h, hb);
-                cm_prefetch<EDGE, ZERO>(g, pxi, pyi, (size_t)((long long)min(rr + 2 + CM_PF, ny - 1) * nx + ibase), L);
-                cm_load<EDGE, ZERO>(nA, g, pxi, pyi, (size_t)((long long)(rr + 2) * nx + ibase), L);
-                fast_row(nB, rr + 1, hb, h);
+#pragma unroll
+            for (int v = 0; v < 2; ++v) { hb[0].px[v] = nxt.px[v]; hb[0].py[v] = nxt.py[v]; hb[0].g[v] = nxt.g[v]; }   // raw row r
+            const long long o1 = (long long)(r + 1) * nx + ibase, os = (long long)(r - T) * nx + ibase;
+            const double *gl = g + o1, *pxl = pxi + o1, *pyl = pyi + o1;        // next row to load
+            double *pxs = pxo + os, *pys = pyo + os, *fs = EMIT ? f + os : nullptr;   // next row to store
+            const size_t pfo = (size_t)CM_PF * nx;
+            auto fast_row = [&](int rr, CmLv (&ho)[T], CmLv (&hn)[T]) {
+                hn[0].g[0] *= invlam; hn[0].g[1] *= invlam;                     // g / lambda (:124)
+                CmLv top;
+                cm_step2<EDGE>(ho[0], hn[0], T > 1 ? hn[T > 1 ? 1 : 0] : top, L, tau, err[0]);
+                // ho[0] is dead from here on: row rr + 1 lands in it
+                if (rr + 1 + CM_PF < ny) cm_prefetch<EDGE, ZERO>(gl, pxl, pyl, pfo, L);
+                {
+                    CmPk ld;
+                    cm_load<EDGE, ZERO>(ld, gl, pxl, pyl, 0, L);
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) { ho[0].px[v] = ld.px[v]; ho[0].py[v] = ld.py[v]; ho[0].g[v] = ld.g[v]; }
+                }
+                gl += nx; pxl += nx; pyl += nx;
+#pragma unroll
+                for (int s = 1; s < T; ++s) {
+                    if (s + 1 < T) cm_step2<EDGE>(ho[s], hn[s], hn[s + 1 < T ? s + 1 : s], L, tau, err[s]);
+                    else cm_step2<EDGE>(ho[s], hn[s], top, L, tau, err[s]);
+                }
+                CmPk p;
+#pragma unroll
+                for (int v = 0; v < 2; ++v) { p.px[v] = top.px[v]; p.py[v] = top.py[v]; p.g[v] = top.g[v]; }
+                if (EMIT) cm_emit<EDGE, EMIT>(p, prevpy, fs, pxs, pys, 0, L, lambda, true, false);
+                else cm_store<EDGE>(p, pxs, pys, 0, L);
+                pxs += nx; pys += nx;
+                if (EMIT) fs += nx;
             };
-            // (four rows per trip would halve the ~60 register moves ptxas leaves at the back edge, but the
-            // loop then outgrows the instruction cache close to the SMSP: ncu shows no_instruction stalls
-            // and no net gain)
-            for (; r + 1 <= fast_hi; r += 2) trip(r);
-            nxt = nA;                               // row r, for the generic iterations that follow
+            // (four rows per trip would halve the register moves ptxas leaves at the back edge, but the loop
+            // then outgrows the instruction cache close to the SMSP: ncu shows no_instruction stalls and no
+            // net gain)
+            for (; r + 1 <= fast_hi; r += 2) { fast_row(r, h, hb); fast_row(r + 1, hb, h); }
+#pragma unroll
+            for (int v = 0; v < 2; ++v) { nxt.px[v] = hb[0].px[v]; nxt.py[v] = hb[0].py[v]; nxt.g[v] = hb[0].g[v]; }   // raw row r
             // the fast rows add their err terms unmasked: lanes outside the output region hold 0
             if (!L.central) {
 #pragma unroll
