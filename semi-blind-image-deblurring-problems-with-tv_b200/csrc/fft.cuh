@@ -360,7 +360,9 @@ struct ColArgs {
     double mu;              // COL_FILTER: the ADMM penalty in 1/(|H|^2 + mu)   (run_Gaussian_demo.m:224)
 };
 
-template <int N, int MODE>
+// SYM: psf_size == 7, point-symmetric PSF evaluation (psf_sym3); otherwise the Horner form.  A compile-time
+// switch: with both forms in one kernel the 16-times unrolled epilogue doubles to 160 KB of code.
+template <int N, int MODE, bool SYM>
 __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
     extern __shared__ double2 fsm[];
     __shared__ double2 coefS[8][3][MAXT];
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
             const int j = e % a.t, m = (e / a.t) % 3, c = e / (3 * a.t);
             const int k = min(k0 + c, a.nk - 1);
             const double2* cf = a.coef + ((size_t)m * a.nk + k) * MAXT;
-            if (a.t == 7) {                          // point-symmetric form, see psf_sym3
+            if (SYM) {                               // point-symmetric form, see psf_sym3
                 const double2 wk = __ldg(a.tw_x + k);
                 const double2 wk3 = cmul(cmul(wk, wk), wk);
                 if (j <= 3) coefS[c][m][j] = psf_sym3_coef(cf, make_double2(wk3.x, -wk3.y), j);
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
             }
         }
     }
-    const bool sym = a.t == 7;
+    constexpr bool sym = SYM;
     __syncthreads();
 
     const bool active = threadIdx.x < C * TL;

@@ -439,8 +439,12 @@ void cols(sbd_ctx* c, const double2* in, double2* out, int batch, int opsel = 0)
     const size_t smem = c->cols_smem;
     dim3 g(batch, c->ntiles * (c->colsC / c->colsKC));
     switch (c->ny) {
-#define X(N) case N: set_smem(k_cols<N, MODE>, smem); a.pf = resident_blocks(c, k_cols<N, MODE>, c->colsT, smem); \
-        k_cols<N, MODE><<<g, c->colsT, smem, c->stream>>>(a); break;
+#define X(N) case N: \
+        if (c->t == 7) { set_smem(k_cols<N, MODE, true>, smem); a.pf = resident_blocks(c, k_cols<N, MODE, true>, c->colsT, smem); \
+                         k_cols<N, MODE, true><<<g, c->colsT, smem, c->stream>>>(a); } \
+        else { set_smem(k_cols<N, MODE, false>, smem); a.pf = resident_blocks(c, k_cols<N, MODE, false>, c->colsT, smem); \
+               k_cols<N, MODE, false><<<g, c->colsT, smem, c->stream>>>(a); } \
+        break;
         SBD_FFT_SIZES(X)
 #undef X
         default: throw Error{SBD_E_UNSUPPORTED, "cols: unsupported size"};
