@@ -173,6 +173,17 @@ __device__ __forceinline__ void stage_store(int tl, const double2 (&v)[16], Dst 
     }
 }
 
+// the operand fetch of a first stage on its own (same order as stage_load<N, R, 1>)
+template <int N, int R, class Src>
+__device__ __forceinline__ void stage_fetch(int tl, double2 (&v)[16], Src src) {
+    constexpr int M = 16 / R, TL = N / 16, Q = N / R;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[m * R + r] = src(tl + m * TL + r * Q);
+    }
+}
+
 // Full transform of the line(s) a block holds.  src0 feeds the first stage, dstL
 // receives the last stage; the stage boundaries go through the shared-memory
 // line `s` (padded, element stride `cs`, i.e. position p lives at s[fft_pad(p)*cs]).
@@ -414,10 +425,18 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
         }
     }
     constexpr bool sym = SYM;
-    __syncthreads();
-
     const bool active = threadIdx.x < C * TL;
     const int c = threadIdx.x & (C - 1), tl = threadIdx.x >> a.logC;
+    // The coefficients are first needed behind a stage barrier, except by the gradient pass, whose first
+    // stage multiplies by H: there the raw operands are fetched BEFORE the block waits for the handful of
+    // threads that build the coefficients (ncu: that barrier alone was 13 % of the pass's stall samples; taking it
+    // out of the way is free but gains nothing measurable - the wait moves to the first use of the operands).
+    double2 raw[16];
+    if (MODE == COL_MUL_INV) {
+        if (active) stage_fetch<N, FftPlan<N>::R0>(tl, raw, [&](int q) { return __ldg(in + (size_t)q * LC + c); });
+        __syncthreads();
+    }
+
     const int k = k0 + c;
     const bool kin = k < a.nk;                       // the last tile may be partly empty
     double2* line = fsm + c;                         // element stride C between positions
@@ -432,8 +451,11 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
         return psf_horner(coefS[c][m], a.t, w);
     };
 
+    int nraw = 0;                                    // stage_load asks for the operands in stage_fetch order
     auto gsrc = [&](int q) {
-        double2 v = __ldg(in + (size_t)q * LC + c);
+        double2 v;
+        if (MODE == COL_MUL_INV) v = raw[nraw++];
+        else v = __ldg(in + (size_t)q * LC + c);
         if (MODE == COL_MUL_INV) {
             const double2 w = __ldg(a.tw + q);
             const double2 H = kern(0, w);
