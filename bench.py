@@ -287,10 +287,13 @@ def run_ours(args, rank, world, local_rank):
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
-    # block plan of sbd.cu chambolle(): K = 25 -> six 4-level launches + a one-level tail launch that also writes
-    # the prox output; phase "chambolle_sweeps" times the 4-level launches (and their no-op redo launches) only
+    # block plan of sbd.cu chambolle(): K = 25 -> four 4-level launches + three 3-level launches, the last of which
+    # also writes the prox output; phase "chambolle_sweeps" times the 4-level launches (and their no-op redo launches) only
     a4, r4 = CHAMBOLLE_K // 4, CHAMBOLLE_K % 4
-    n4 = a4 if r4 in (1, 3) else a4 - 1
+    if r4 == 1 and a4 >= 2 and os.environ.get("SBD_CHAMB_PLAN33", "1") != "0":
+        n4 = a4 - 2
+    else:
+        n4 = a4 if r4 in (1, 3) else a4 - 1
     n_prox = int(phases["chambolle_sweeps"][1])
     launches_timed = n_prox * n4
     sweep_ms = phases["chambolle_sweeps"][0] / max(launches_timed, 1)
@@ -317,9 +320,11 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_ms,
                      "launches_timed": launches_timed, "sweeps_executed_chain0": sweeps_executed,
-                     "note": "algorithmic bytes = 40 B/pixel/sweep x sweeps per launch; temporal blocking keeps the T "
-                             "sweep levels in registers, so measured DRAM traffic per launch (ncu, `traffic`) is ~1/4 of "
-                             "it and the model-based fraction exceeds 1; the kernel is fp64-pipe bound (profiles/)"},
+                     "note": "algorithmic bytes = 40 B/pixel/sweep x the 4 sweeps of one launch; temporal blocking keeps the 4 "
+                             "sweep levels in registers, so the measured DRAM traffic per launch (ncu, `traffic`) is ~1/4 of it and "
+                             "the model-based fraction exceeds 1. What bounds the kernel instead is fp64 instruction issue: ncu shows "
+                             "the fp64 pipe 60 % active, ~91 % of the issue bound calibrated by tools/fp64_microbench.cu "
+                             "(profiles/r01_ncu_summary.md, profiles/r01_fp64_microbench.txt, DESIGN.md section 5)"},
         "fused_step": {"alg_bytes_per_chain_step": alg_bytes_per_chain_step(npix), "achieved_gbs_per_gpu": step_gbs / world,
                        "frac_of_hbm_peak": step_gbs / world / peak,
                        "phase_ms_per_step": {("chambolle_total" if k_ == "chambolle_other" else k_): v_[0] / K

@@ -76,7 +76,7 @@ struct sbd_ctx {
     int tvV = 1, tv_gx = 1, tv_gy = 1, tv_seg = 8, tv_parts = 1;
     int sm_count = 148, fft_pf = 1;                                     // L2 prefetch distance of the FFT passes
     int cmT = 5, cm_strips = 1, cm_gx = 1, cm_gy = 1, cm_seg = 128;     // fused Chambolle geometry
-    bool cm_pipe = false, cm_emit = true;
+    bool cm_pipe = false, cm_emit = true, cm_plan33 = true;
     double salsa_mu = 0.0;
     int cm_minb = 3;
     int rowsLP = 1, rowsT = 32, colsC = 2, colsLogC = 1, colsT = 32, ntiles = 1;
@@ -186,6 +186,7 @@ void set_geometry(sbd_ctx* c, int batch) {
         if (sg == 8 && (long long)c->cm_gx * ((ny + 7) / 8) * batch < 2 * 148) sg = 4;      // less than two blocks per SM
         if (const char* e = getenv("SBD_CHAMB_SEG")) sg = std::max(1, atoi(e));
         if (const char* e = getenv("SBD_CHAMB_EMIT")) c->cm_emit = atoi(e) != 0;
+        if (const char* e = getenv("SBD_CHAMB_PLAN33")) c->cm_plan33 = atoi(e) != 0;
         c->cm_seg = sg;
         c->cm_gy = (ny + sg - 1) / sg;
     }
@@ -307,11 +308,14 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
         // blocks of fused sweeps; each block = main launch + redo launch (a no-op unless the reference's
         // stop test fired inside the block).  4-level blocks are the most efficient; the block planned
         // last is an odd one (3 or 1 levels), because odd blocks have a pixel of lateral validity to
-        // spare and can write the prox output themselves (EMIT, tv_multi.cuh): K = 25 -> 4 x6, 1.
+        // spare and can write the prox output themselves (EMIT, tv_multi.cuh).  K = 4k+1 runs as 4 x(k-2), 3 x3
+        // rather than 4 x k, 1: the one-level tail is a full memory pass for a single sweep (K = 25: 10.12 vs
+        // 10.22 ms per prox of 8 chains at 4096^2; SBD_CHAMB_PLAN33=0 restores the other plan).
         std::vector<int> plan;
         if (c->cmT == 4) {
             const int a = maxiter / 4, r = maxiter % 4;
-            if (r == 1 || r == 3) { plan.assign(a, 4); plan.push_back(r); }
+            if (r == 1 && a >= 2 && c->cm_plan33) { plan.assign(a - 2, 4); plan.insert(plan.end(), 3, 3); }   // 4k+1 = 4(k-2) + 3*3
+            else if (r == 1 || r == 3) { plan.assign(a, 4); plan.push_back(r); }
             else if (r == 2) { if (a > 0) { plan.assign(a - 1, 4); plan.push_back(3); plan.push_back(3); } else plan.push_back(3); }
             else { plan.assign(a - 1, 4); plan.push_back(3); plan.push_back(1); }      // maxiter >= 4 here
         } else {
