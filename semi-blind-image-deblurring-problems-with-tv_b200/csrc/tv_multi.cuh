@@ -18,7 +18,7 @@
 // f = g - lambda*div p (chambolle_prox_TV_stop.m:134) from the rows its top level
 // emits, instead of a separate pass over (g, px, py).  div p needs p one pixel to
 // the left and one row above the emitted row, so this needs one pixel of lateral
-// validity to spare (HL > nlev: the 5-level kernel has it) and the march starts
+// validity to spare (HL > nlev: blocks with an odd number of levels have it) and the march starts
 // one row earlier.  EMIT = 2 additionally skips the store of the dual pair (the
 // SAPG loop starts every prox from zero and never reads it back).
 #pragma once
