@@ -105,6 +105,8 @@ int sbd_blur_dev(sbd_ctx* ctx, const double* d_x, const double psi[2], int op, d
  *                maxiter < 1 is an error (the reference leaves MaxIter
  *                undefined, :80/:131).  Each image of the batch stops on its
  *                own `err <= tol` test exactly like the reference loop.
+ *                sbd_tvprox_dev: d_f must not overlap d_g (the last fused block
+ *                writes f while other blocks still read g) - SBD_E_INVALID otherwise.
  * ---------------------------------------------------------------------- */
 int sbd_tvnorm(sbd_ctx* ctx, const double* x, double* out, int batch);
 int sbd_diff(sbd_ctx* ctx, const double* x, int axis, double* out, int batch);
@@ -261,6 +263,24 @@ int sbd_comm_destroy(sbd_ctx* ctx);
 int sbd_set_profile(sbd_ctx* ctx, int on);
 int sbd_phase_times(const sbd_ctx* ctx, double ms[SBD_N_PHASES], long long calls[SBD_N_PHASES]);
 const char* sbd_phase_name(int i);
+
+/* ------------------------------------------------------------------------
+ * Launch-geometry control (no reference counterpart: the reference has no
+ * launch geometry).  Used by the parity tests to pin the production geometry
+ * of the fused Chambolle kernel at sizes the oracle finishes quickly, and by
+ * tuning runs.  Options (value -1 / 0 restores the automatic choice):
+ *   "chamb_seg"    rows per marching-warp segment of the fused Chambolle kernel
+ *   "chamb_levels" sweeps fused per launch: 4 (default), 3, 1 = single-sweep kernel
+ *   "chamb_emit"   0: separate prox-output pass instead of the tail block writing f
+ *   "chamb_plan33" 0: plan K = 4k+1 as 4 x k, 1 instead of 4 x (k-2), 3 x 3
+ *   "tv_seg"       rows per segment of the TVnorm / single-sweep / output kernels
+ *   "geom_chains"  derive the geometry from this many chains instead of the batch
+ * sbd_get_geometry: out = {levels, chamb_seg, chamb_grid_x, chamb_grid_y,
+ *                          tv_seg, tv_grid_x, tv_grid_y, rows_line_pairs}
+ * ---------------------------------------------------------------------- */
+#define SBD_N_GEOM 8
+int sbd_set_option(sbd_ctx* ctx, const char* name, int value);
+int sbd_get_geometry(sbd_ctx* ctx, int batch, int out[SBD_N_GEOM]);
 
 #ifdef __cplusplus
 }

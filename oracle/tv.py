@@ -6,7 +6,55 @@ Oracle (test infrastructure).  numpy float64 restatement of
   utils/chambolle_prox_TV_stop.m
 """
 
+import ctypes as _C
+import os as _os
+
 import numpy as np
+
+# --------------------------------------------------------------------------
+# optional plain-C fast path for LARGE images (oracle/c/tv_oracle.c, built by
+# `make -C oracle/c` / __graft_entry__.build()).  Same operations in the same
+# floating-point order as the numpy code below, element for element; only the
+# order of the err / TV sums differs (tests/test_oracle.py pins one against the
+# other).  ACCEL: "auto" = use it for images of >= ACCEL_MIN_PIXELS pixels when
+# the library is there, False = numpy only, True = always (raises if missing).
+# --------------------------------------------------------------------------
+ACCEL = "auto"
+ACCEL_MIN_PIXELS = 512 * 512
+_clib = None
+
+
+def _c():
+    global _clib
+    if _clib is None:
+        path = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "c", "_build", "liboracle_tv.so")
+        if not _os.path.exists(path):
+            _clib = False
+            return _clib
+        lib = _C.CDLL(path)
+        dp = _C.POINTER(_C.c_double)
+        lib.oc_chambolle.restype = _C.c_int
+        lib.oc_chambolle.argtypes = [dp, _C.c_long, _C.c_long, _C.c_double, _C.c_int, _C.c_double, _C.c_double,
+                                     dp, dp, dp, dp]
+        lib.oc_tvnorm.restype = _C.c_double
+        lib.oc_tvnorm.argtypes = [dp, _C.c_long, _C.c_long]
+        _clib = lib
+    return _clib
+
+
+def _use_c(npix):
+    if ACCEL is False:
+        return False
+    lib = _c()
+    if ACCEL is True:
+        if not lib:
+            raise RuntimeError("oracle/c/_build/liboracle_tv.so is not built (make -C oracle/c)")
+        return True
+    return bool(lib) and npix >= ACCEL_MIN_PIXELS
+
+
+def _dp(a):
+    return a.ctypes.data_as(_C.POINTER(_C.c_double))
 
 
 # --------------------------------------------------------------------------
@@ -74,6 +122,10 @@ def diffv(x):
 
 def TVnorm(x):
     """utils/TVnorm.m:1-2."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 2 and _use_c(x.size):
+        xc = np.ascontiguousarray(x)
+        return float(_c().oc_tvnorm(_dp(xc), xc.shape[0], xc.shape[1]))
     return float(np.sum(np.sum(np.sqrt(diffh(x) ** 2 + diffv(x) ** 2), axis=0)))
 
 
@@ -130,6 +182,18 @@ def chambolle_prox_TV_stop(g, *varargin, return_info=False):
                 raise ValueError("Wrong size of the dual variables")
             py = val[:, M:].copy()                              # :106 (splits at M: square only, Q5)
             px = val[:, :M].copy()                              # :107
+    if MaxIter is not None and MaxIter >= 1 and g.ndim == 2 and min(g.shape) >= 2 and _use_c(g.size):
+        gc = np.ascontiguousarray(g)
+        px = np.ascontiguousarray(px, dtype=np.float64).copy(); py = np.ascontiguousarray(py, dtype=np.float64).copy()
+        f = np.empty_like(gc)
+        e = _C.c_double()
+        k = _c().oc_chambolle(_dp(gc), gc.shape[0], gc.shape[1], lam, MaxIter, tol, tau, _dp(px), _dp(py), _dp(f),
+                              _C.byref(e))
+        if k < 0:
+            raise MemoryError("oc_chambolle")
+        if return_info:
+            return f, px, py, k, float(e.value)
+        return f, px, py
     err = np.nan
     while True:                                                 # :120
         k += 1

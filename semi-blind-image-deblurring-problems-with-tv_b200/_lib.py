@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsbd.so")
 
 SBD_N_PHASES = 8
+SBD_N_GEOM = 8
 SBD_NCCL_ID_BYTES = 128
 
 c_double_p = C.POINTER(C.c_double)
@@ -95,6 +96,8 @@ SIGNATURES = {
     "sbd_phase_times": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_longlong)]),
     "sbd_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "sbd_phase_name": (C.c_char_p, [C.c_int]),
+    "sbd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "sbd_get_geometry": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
 }
 
 _lib = None

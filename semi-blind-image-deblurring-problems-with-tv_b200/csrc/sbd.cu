@@ -83,6 +83,15 @@ struct sbd_ctx {
     int colsKC = 2, colsLogKC = 1;     // columns per block of the column pass (<= colsC, the layout tile width)
     size_t rows_smem = 0, cols_smem = 0;
     int geom_batch = -1;
+    // launch-geometry overrides (sbd_set_option; -1 = automatic).  Seeded from the SBD_* environment at sbd_create.
+    int opt_chamb_seg = -1, opt_chamb_T = -1, opt_tv_seg = -1, opt_chamb_emit = -1, opt_chamb_plan33 = -1;
+    // The segment lengths fix the summation order of the TV-norm and err_k partial sums, so they must not depend
+    // on how many of a run's chains happen to live on this GPU: inside a SAPG run the geometry is derived from
+    // the TOTAL number of chains over all ranks (0 = use the batch of the call).
+    int geom_total = 0;
+    // per-context (= per-device) caches of kernel attributes: cudaFuncSetAttribute is per device
+    std::map<const void*, size_t> smem_optin;
+    std::map<std::pair<const void*, size_t>, int> resident_cache;
 
     // device buffers
     double2 *tw_nx = nullptr, *tw_ny = nullptr;
@@ -158,7 +167,8 @@ void free_ws(sbd_ctx* c) {
 }
 
 // choose launch geometry for a batch of `batch` images
-void set_geometry(sbd_ctx* c, int batch) {
+void set_geometry(sbd_ctx* c, int batch_local) {
+    const int batch = std::max(batch_local, c->geom_total);
     if (c->geom_batch == batch) return;
     const int nx = c->nx, ny = c->ny;
     c->tvV = (nx % 2 == 0 && nx >= 64) ? 2 : 1;
@@ -166,15 +176,14 @@ void set_geometry(sbd_ctx* c, int batch) {
     c->tv_gx = (strips + TV_WARPS - 1) / TV_WARPS;
     int seg = 64;
     while (seg > 8 && (long long)c->tv_gx * ((ny + seg - 1) / seg) * batch < 4 * 148) seg /= 2;
-    if (const char* e = getenv("SBD_TV_SEG")) seg = std::max(1, atoi(e));
+    if (c->opt_tv_seg > 0) seg = c->opt_tv_seg;
     c->tv_seg = seg;
     c->tv_gy = (ny + seg - 1) / seg;
     c->tv_parts = c->tv_gx * c->tv_gy;
     {   // fused multi-sweep Chambolle kernel (tv_multi.cuh): T levels, strips of 64 - 2*HL output pixels
         int T = 4;
-        if (const char* e = getenv("SBD_CHAMB_T")) T = atoi(e);
+        if (c->opt_chamb_T > 0) T = c->opt_chamb_T;
         if (nx % 2 != 0 || nx < 8) T = 1;           // pairs of pixels must be 16-byte aligned
-        if (const char* e = getenv("SBD_CHAMB_PIPE")) c->cm_pipe = atoi(e) != 0;
         c->cmT = (T == 3 || T == 4) ? T : 1;
         const int HL = (c->cmT + 1) & ~1, WO = 64 - 2 * HL;
         c->cm_strips = (nx + WO - 1) / WO;
@@ -184,9 +193,9 @@ void set_geometry(sbd_ctx* c, int batch) {
         // parallelism (256^2, one chain: 4-row segments are 10 % faster than 8-row ones)
         while (sg > 8 && (long long)c->cm_gx * ((ny + sg - 1) / sg) * batch < 6 * 148) sg /= 2;
         if (sg == 8 && (long long)c->cm_gx * ((ny + 7) / 8) * batch < 2 * 148) sg = 4;      // less than two blocks per SM
-        if (const char* e = getenv("SBD_CHAMB_SEG")) sg = std::max(1, atoi(e));
-        if (const char* e = getenv("SBD_CHAMB_EMIT")) c->cm_emit = atoi(e) != 0;
-        if (const char* e = getenv("SBD_CHAMB_PLAN33")) c->cm_plan33 = atoi(e) != 0;
+        if (c->opt_chamb_seg > 0) sg = c->opt_chamb_seg;
+        if (c->opt_chamb_emit >= 0) c->cm_emit = c->opt_chamb_emit != 0;
+        if (c->opt_chamb_plan33 >= 0) c->cm_plan33 = c->opt_chamb_plan33 != 0;
         c->cm_seg = sg;
         c->cm_gy = (ny + sg - 1) / sg;
     }
@@ -300,6 +309,7 @@ void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const do
 // zero_start: the dual pair starts from zero (px0/py0 are then neither read nor need to be cleared
 // when the fused kernel runs; the single-sweep path clears them itself)
 void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, bool zero_start, bool keep_duals = true) {
+    SBD_REQUIRE(maxiter >= 1, SBD_E_INVALID, "chambolle: maxiter must be >= 1");       // the block plan below relies on it
     k_chamb_reset<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->chst, batch);
     LAUNCH_CHECK(c);
     dim3 grid(c->tv_gx, c->tv_gy, batch);
@@ -369,9 +379,9 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
 }
 
 template <typename K>
-void set_smem(K kernel, size_t bytes) {
-    // opt in to > 48 KB of dynamic shared memory, once per (kernel, size)
-    static std::map<const void*, size_t> done;
+void set_smem(sbd_ctx* c, K kernel, size_t bytes) {
+    // opt in to > 48 KB of dynamic shared memory, once per (context = device, kernel, size)
+    std::map<const void*, size_t>& done = c->smem_optin;
     const void* key = reinterpret_cast<const void*>(kernel);
     auto it = done.find(key);
     if (it != done.end() && it->second >= bytes) return;
@@ -383,7 +393,7 @@ void set_smem(K kernel, size_t bytes) {
 // blocks of `kernel` resident on the whole device = the L2 prefetch distance of the FFT passes
 template <typename K>
 int resident_blocks(sbd_ctx* c, K kernel, int threads, size_t smem) {
-    static std::map<std::pair<const void*, size_t>, int> cache;
+    std::map<std::pair<const void*, size_t>, int>& cache = c->resident_cache;
     const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), smem * 4096 + (size_t)threads);
     auto it = cache.find(key);
     if (it != cache.end()) return c->fft_pf ? it->second : 0;
@@ -406,7 +416,7 @@ void rows_fwd(sbd_ctx* c, const double* x, double2* spec, int batch) {
     dim3 g(c->ny / 2 / c->rowsLP, batch);
     const SpecGeom sg = spec_geom(c);
     switch (c->nx) {
-#define X(N) case N: set_smem(k_rows_fwd<N>, smem); \
+#define X(N) case N: set_smem(c, k_rows_fwd<N>, smem); \
         k_rows_fwd<N><<<g, c->rowsT, smem, c->stream>>>(x, spec, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx, \
                                                         resident_blocks(c, k_rows_fwd<N>, c->rowsT, smem)); break;
         SBD_FFT_SIZES(X)
@@ -421,7 +431,7 @@ void rows_inv(sbd_ctx* c, const double2* spec, double* out, int batch) {
     dim3 g(c->ny / 2 / c->rowsLP, batch);
     const SpecGeom sg = spec_geom(c);
     switch (c->nx) {
-#define X(N) case N: set_smem(k_rows_inv<N>, smem); \
+#define X(N) case N: set_smem(c, k_rows_inv<N>, smem); \
         k_rows_inv<N><<<g, c->rowsT, smem, c->stream>>>(spec, out, sg, c->rowsLP, c->npix, c->spec_elems, c->tw_nx); break;
         SBD_FFT_SIZES(X)
 #undef X
@@ -444,9 +454,9 @@ void cols(sbd_ctx* c, const double2* in, double2* out, int batch, int opsel = 0)
     dim3 g(batch, c->ntiles * (c->colsC / c->colsKC));
     switch (c->ny) {
 #define X(N) case N: \
-        if (c->t == 7) { set_smem(k_cols<N, MODE, true>, smem); a.pf = resident_blocks(c, k_cols<N, MODE, true>, c->colsT, smem); \
+        if (c->t == 7) { set_smem(c, k_cols<N, MODE, true>, smem); a.pf = resident_blocks(c, k_cols<N, MODE, true>, c->colsT, smem); \
                          k_cols<N, MODE, true><<<g, c->colsT, smem, c->stream>>>(a); } \
-        else { set_smem(k_cols<N, MODE, false>, smem); a.pf = resident_blocks(c, k_cols<N, MODE, false>, c->colsT, smem); \
+        else { set_smem(c, k_cols<N, MODE, false>, smem); a.pf = resident_blocks(c, k_cols<N, MODE, false>, c->colsT, smem); \
                k_cols<N, MODE, false><<<g, c->colsT, smem, c->stream>>>(a); } \
         break;
         SBD_FFT_SIZES(X)
@@ -515,6 +525,28 @@ int sbd_set_profile(sbd_ctx* ctx, int on) {
     return SBD_OK;
 }
 
+int sbd_set_option(sbd_ctx* c, const char* name, int value) {
+    if (!c || !name) return SBD_E_INVALID;
+    const std::string n(name);
+    if (n == "chamb_seg") c->opt_chamb_seg = value;
+    else if (n == "chamb_levels") c->opt_chamb_T = value;
+    else if (n == "tv_seg") c->opt_tv_seg = value;
+    else if (n == "chamb_emit") c->opt_chamb_emit = value;
+    else if (n == "chamb_plan33") c->opt_chamb_plan33 = value;
+    else if (n == "geom_chains") c->geom_total = std::max(value, 0);
+    else { c->err = "sbd_set_option: unknown option '" + n + "'"; return SBD_E_INVALID; }
+    c->geom_batch = -1;             // recomputed by the next call
+    return SBD_OK;
+}
+
+int sbd_get_geometry(sbd_ctx* c, int batch, int out[SBD_N_GEOM]) {
+    if (!c || !out || batch < 1) return SBD_E_INVALID;
+    set_geometry(c, batch);
+    out[0] = c->cmT; out[1] = c->cm_seg; out[2] = c->cm_gx; out[3] = c->cm_gy;
+    out[4] = c->tv_seg; out[5] = c->tv_gx; out[6] = c->tv_gy; out[7] = c->rowsLP;
+    return SBD_OK;
+}
+
 int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, double phi,
                int max_batch, int device) {
     sbd_ctx* c = nullptr;
@@ -569,6 +601,12 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
             c->cols_smem = (size_t)KC * le_y * 16;
         }
         c->spec_elems = (size_t)c->ntiles * cols * c->colsC;
+        {
+            auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+            c->opt_chamb_seg = env_int("SBD_CHAMB_SEG", -1); c->opt_chamb_T = env_int("SBD_CHAMB_T", -1);
+            c->opt_tv_seg = env_int("SBD_TV_SEG", -1); c->opt_chamb_emit = env_int("SBD_CHAMB_EMIT", -1);
+            c->opt_chamb_plan33 = env_int("SBD_CHAMB_PLAN33", -1);
+        }
         c->profile = getenv("SBD_PROFILE") && atoi(getenv("SBD_PROFILE")) != 0;
         SBD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         {
@@ -740,6 +778,11 @@ int sbd_tvprox_dev(sbd_ctx* c, const double* d_g, double lambda, int maxiter, do
     SBD_REQUIRE(d_g && d_f && batch >= 1 && batch <= c->max_batch, SBD_E_INVALID, "sbd_tvprox: bad argument");
     SBD_REQUIRE(maxiter >= 1, SBD_E_INVALID,
                 "sbd_tvprox: 'maxiter' is required (the reference leaves MaxIter undefined without it)");
+    {   // the tail block writes f while other blocks still read g (and its halo): no in-place use
+        const char *g0 = (const char*)d_g, *f0 = (const char*)d_f;
+        const size_t bytes = sizeof(double) * (size_t)batch * c->npix;
+        SBD_REQUIRE(f0 + bytes <= g0 || g0 + bytes <= f0, SBD_E_INVALID, "sbd_tvprox_dev: d_f must not overlap d_g");
+    }
     SBD_CUDA(cudaSetDevice(c->device));
     ensure_ws(c, batch);
     set_chamb_options(c, lambda, maxiter, tol, tau);
@@ -1079,6 +1122,9 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     const int ntot = std::max(prm->total_chains, nch);
     if (c->comm) SBD_REQUIRE(ntot == nch * c->nranks, SBD_E_INVALID, "sbd_sapg_run: total_chains must be n_chains * nranks");
     else SBD_REQUIRE(ntot == nch, SBD_E_COMM, "sbd_sapg_run: total_chains > n_chains needs sbd_comm_init");
+    // geometry (= summation order of the partial sums) from the total chain count: bit-identical for any sharding
+    struct GeomReset { sbd_ctx* c; int old; ~GeomReset() { c->geom_total = old; c->geom_batch = -1; } } geom_reset{c, c->geom_total};
+    if (c->geom_total < ntot) { c->geom_total = ntot; c->geom_batch = -1; }
     ensure_ws(c, nch);
     cudaStream_t s = c->stream;
     for (int i = 0; i < SBD_N_PHASES; ++i) { c->phase_ms[i] = 0.0; c->phase_calls[i] = 0; }

@@ -12,7 +12,13 @@
 // The stop test of the reference (err_k <= tol, :128,:131) is evaluated after
 // the kernel for each of the T sweeps in order (speculation): if it fires at
 // sweep s < T the block is re-run from the same input with s levels ("redo"
-// launch, a no-op otherwise), so the result is exactly the reference's.
+// launch, a no-op otherwise), so the sweep count k and the dual pair are the
+// reference's.  Arithmetic tolerance: sqrt and the reciprocal come from MUFU
+// seeds plus one third-order step (<= 1 ulp each, cm_core) and FMA contraction
+// is on, so p differs from an IEEE sqrt/divide evaluation (k_chamb_sweep, the
+// T = 1 fallback) by ~1 ulp per sweep; the two paths are not bitwise equal and
+// an err_k within ~1e-15 relative of tol may decide the stop test differently
+// (tests/test_gpu_chambolle_prod.py::test_fused_vs_single_sweep).
 //
 // EMIT: the block that is planned to be the last one also forms the prox output
 // f = g - lambda*div p (chambolle_prox_TV_stop.m:134) from the rows its top level

@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import lib, sbd_params, sbd_traces, SbdError, c_double_p, SBD_N_PHASES
+from ._lib import lib, sbd_params, sbd_traces, SbdError, c_double_p, SBD_N_PHASES, SBD_N_GEOM
 
 GAUSSIAN, MOFFAT, LAPLACE = 0, 1, 2
 K_PSF, K_DPSI0, K_DPSI1 = 0, 1, 2
@@ -84,6 +84,17 @@ class Engine:
 
     def set_profile(self, on=True):
         self._check(lib.sbd_set_profile(self._h, int(bool(on))))
+
+    def set_option(self, name, value):
+        """Launch-geometry override (include/sbd.h: sbd_set_option); -1 restores the automatic choice."""
+        self._check(lib.sbd_set_option(self._h, name.encode(), int(value)))
+
+    def geometry(self, batch=1):
+        """dict of the launch geometry libsbd would use for a batch of `batch` images."""
+        out = (C.c_int * SBD_N_GEOM)()
+        self._check(lib.sbd_get_geometry(self._h, int(batch), out))
+        keys = ("levels", "chamb_seg", "chamb_grid_x", "chamb_grid_y", "tv_seg", "tv_grid_x", "tv_grid_y", "rows_line_pairs")
+        return dict(zip(keys, list(out)))
 
     def phase_times(self):
         """{phase: (milliseconds, event pairs)} of the last run's main loop."""

@@ -2,12 +2,16 @@
 reference's own definitions and known-answer values.  The golden
 fixtures produced by executing the reference .m files are checked in
 tests/test_oracle_golden.py."""
+import os
+
 import numpy as np
 import pytest
 
 from conftest import rel, kat_image
 import oracle
 from oracle import psf as P, tv, operators as OP, sapg, philox, metrics
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_psf_normalised_and_known_taps():
@@ -153,3 +157,40 @@ def test_sapg_quirks_small():
     for ka, kb in (("thetas", "thetas"), ("sigmas", "sigmas"), ("logPiTraceX", "logPiTraceX")):
         assert rel(rb[kb], ra[ka]) < 1e-13
     assert rel(rb["psis"][0], ra["w1s"]) < 1e-13
+
+
+# ---------------------------------------------------------------- plain-C fast path of the TV oracle
+@pytest.mark.parametrize("shape", [(2, 2), (5, 7), (64, 100), (131, 77), (256, 256)])
+def test_c_tv_oracle_is_the_numpy_oracle(shape):
+    """oracle/c/tv_oracle.c (used for >= 512^2 images) against the numpy restatement that the golden vectors pin:
+    f, px, py bit-identical, k equal, err / TVnorm equal up to the order of the final sum."""
+    import subprocess
+    from oracle import tv
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle", "c")], check=True)
+    rng = np.random.default_rng(shape[0] * 31 + shape[1])
+    g = rng.uniform(0, 255, shape)
+    old = tv.ACCEL
+    try:
+        for lam, K, tol in ((1e-3, 25, 1e-3), (0.3, 25, 1e-3), (2.0, 20, 1e-3), (0.3, 9, 0.0)):
+            tv.ACCEL = False
+            a = tv.chambolle_prox_TV_stop(g, "lambda", lam, "maxiter", K, "tol", tol, return_info=True)
+            tv.ACCEL = True
+            b = tv.chambolle_prox_TV_stop(g, "lambda", lam, "maxiter", K, "tol", tol, return_info=True)
+            assert a[3] == b[3]
+            for i in range(3):
+                assert np.array_equal(a[i], b[i])
+            assert abs(a[4] - b[4]) <= 1e-14 * max(a[4], 1e-300)
+        if shape[0] == shape[1]:
+            dual = rng.uniform(-0.5, 0.5, (shape[0], 2 * shape[1]))
+            tv.ACCEL = False
+            a = tv.chambolle_prox_TV_stop(g, "lambda", 0.7, "maxiter", 10, "tol", 1e-2, "tau", 0.2, "dualvars", dual)
+            tv.ACCEL = True
+            b = tv.chambolle_prox_TV_stop(g, "lambda", 0.7, "maxiter", 10, "tol", 1e-2, "tau", 0.2, "dualvars", dual)
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v)
+        tv.ACCEL = False
+        t0 = tv.TVnorm(g)
+        tv.ACCEL = True
+        assert abs(tv.TVnorm(g) - t0) <= 1e-14 * t0
+    finally:
+        tv.ACCEL = old
