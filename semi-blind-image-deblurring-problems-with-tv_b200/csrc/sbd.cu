@@ -112,6 +112,15 @@ struct sbd_ctx {
     double *post = nullptr;
     int post_batch = 0;
 
+    // per-run scratch kept across calls (a cudaMalloc / cudaFree per sbd_sapg_run costs up to 0.6 s: a free tears down
+    // whatever the driver deferred, e.g. the graphs of the run)
+    double* trace_d = nullptr; size_t trace_d_cap = 0;      // 13 double arrays + delta + err_psf, `trace_len` each
+    int* trace_i = nullptr; size_t trace_i_cap = 0;
+    int allstats_cap = 0;
+    double *sal_aty = nullptr, *sal_u = nullptr, *sal_bu = nullptr, *sal_xt = nullptr;   // SALSA images
+    cudaStream_t copy_stream = nullptr;                     // device -> host copy of the last samples, overlapped
+    cudaEvent_t ev_langevin = nullptr;
+
     // comm
     nccl_comm comm = nullptr;
     int nranks = 1, rank = 0;
@@ -609,6 +618,8 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
         }
         c->profile = getenv("SBD_PROFILE") && atoi(getenv("SBD_PROFILE")) != 0;
         SBD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SBD_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        SBD_CUDA(cudaEventCreateWithFlags(&c->ev_langevin, cudaEventDisableTiming));
         {
             int dev = 0;
             SBD_CUDA(cudaGetDevice(&dev));
@@ -619,6 +630,7 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
         c->ctl = dalloc<Control>(1);
         c->psi_dev = dalloc<double>(2);
         c->ximg = dalloc<double>(c->npix);
+        c->in_y = dalloc<double>(c->npix);          // staging image of the host-pointer entries (not allocated per call)
         SBD_CUDA(cudaMemsetAsync(c->ctl, 0, sizeof(Control), c->stream));
         if (c->pow2) {
             c->tw_nx = dalloc<double2>(rows); c->tw_ny = dalloc<double2>(cols);
@@ -645,6 +657,9 @@ int sbd_destroy(sbd_ctx* c) {
     dfree(c->in_y); dfree(c->in_x0); dfree(c->in_xt);
     dfree(c->tw_nx); dfree(c->tw_ny); dfree(c->taps); dfree(c->coef); dfree(c->ctl); dfree(c->psi_dev);
     dfree(c->ximg); dfree(c->yhat); dfree(c->allstats); dfree(c->post);
+    dfree(c->trace_d); dfree(c->trace_i); dfree(c->sal_aty); dfree(c->sal_u); dfree(c->sal_bu); dfree(c->sal_xt);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_langevin) cudaEventDestroy(c->ev_langevin);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return SBD_OK;
@@ -972,8 +987,13 @@ int sbd_salsa_tv(sbd_ctx* c, const double* y, const double psi[2], double tau, d
         const size_t n = c->npix, bytes = sizeof(double) * n;
         const unsigned gb = (unsigned)((n + 255) / 256);
         const double P = (double)n;
-        d_aty = dalloc<double>(n); d_u = dalloc<double>(n); d_bu = dalloc<double>(n);
-        if (x_true) { d_xt = dalloc<double>(n); SBD_CUDA(cudaMemcpyAsync(d_xt, x_true, bytes, cudaMemcpyHostToDevice, s)); }
+        if (!c->sal_aty) { c->sal_aty = dalloc<double>(n); c->sal_u = dalloc<double>(n); c->sal_bu = dalloc<double>(n); }
+        d_aty = c->sal_aty; d_u = c->sal_u; d_bu = c->sal_bu;
+        if (x_true) {
+            if (!c->sal_xt) c->sal_xt = dalloc<double>(n);
+            d_xt = c->sal_xt;
+            SBD_CUDA(cudaMemcpyAsync(d_xt, x_true, bytes, cudaMemcpyHostToDevice, s));
+        }
         // Y^, ATy = AT(y)                                                        SALSA_v2.m:287
         SBD_CUDA(cudaMemcpyAsync(c->ximg, y, bytes, cudaMemcpyHostToDevice, s));
         psf_from_host(c, psi, c->nk);
@@ -1031,7 +1051,6 @@ int sbd_salsa_tv(sbd_ctx* c, const double* y, const double psi[2], double tau, d
     } catch (const Error& e) {
         rc = fail(c, e);
     }
-    cudaFree(d_aty); cudaFree(d_u); cudaFree(d_bu); cudaFree(d_xt);
     return rc;
 }
 
@@ -1075,17 +1094,13 @@ int sbd_comm_destroy(sbd_ctx* c) {
 // ===========================================================================
 namespace {
 
+// device trace arrays: slices of one block that lives in the context and only ever grows
 struct DevTraces {
     Traces t;
     double* delta = nullptr;
-    std::vector<void*> owned;
-    ~DevTraces() { for (void* p : owned) cudaFree(p); }
-    template <typename T> T* mk(size_t n, cudaStream_t s) {
-        T* p = dalloc<T>(n);
-        owned.push_back(p);
-        SBD_CUDA(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), s));
-        return p;
-    }
+    double* errpsf = nullptr;
+    double* cur = nullptr;
+    double* take(size_t n) { double* p = cur; cur += n; return p; }
 };
 
 // spectral analysis of the current X: tv, X^ (in S1) and the Parseval sums
@@ -1148,26 +1163,30 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     k.dimX = (double)c->npix; k.n_local = nch; k.n_total = ntot;
     k.burnIn = burnIn; k.samples = samples; k.warmup = warmup; k.has_xtrue = d_xtrue != nullptr;
 
-    // device traces
+    // device traces (no allocation in the steady state: the block is kept in the context)
     DevTraces dt;
-    dt.t.logPiWU = dt.mk<double>(std::max(warmup, 1), s);
-    dt.t.thetas = dt.mk<double>(samples, s); dt.t.sigmas = dt.mk<double>(samples, s);
-    dt.t.psi0 = dt.mk<double>(samples, s); dt.t.psi1 = dt.mk<double>(samples, s);
-    dt.t.g_theta = dt.mk<double>(samples, s); dt.t.g_psi0 = dt.mk<double>(samples, s);
-    dt.t.g_psi1 = dt.mk<double>(samples, s); dt.t.g_sigma = dt.mk<double>(samples, s);
-    dt.t.logPi = dt.mk<double>(samples, s); dt.t.gX = dt.mk<double>(samples, s);
-    dt.t.sqerr = dt.mk<double>(samples, s); dt.t.chamb_k = dt.mk<int>(samples, s);
     {
+        const size_t wu = (size_t)std::max(warmup, 1), S = (size_t)samples;
+        const size_t need = wu + 11 * S + (S + 1) + S;
+        if (need > c->trace_d_cap) { dfree(c->trace_d); c->trace_d = dalloc<double>(need); c->trace_d_cap = need; }
+        if (S > c->trace_i_cap) { dfree(c->trace_i); c->trace_i = dalloc<int>(S); c->trace_i_cap = S; }
+        SBD_CUDA(cudaMemsetAsync(c->trace_d, 0, need * sizeof(double), s));
+        SBD_CUDA(cudaMemsetAsync(c->trace_i, 0, S * sizeof(int), s));
+        dt.cur = c->trace_d;
+        dt.t.logPiWU = dt.take(wu);
+        dt.t.thetas = dt.take(S); dt.t.sigmas = dt.take(S); dt.t.psi0 = dt.take(S); dt.t.psi1 = dt.take(S);
+        dt.t.g_theta = dt.take(S); dt.t.g_psi0 = dt.take(S); dt.t.g_psi1 = dt.take(S); dt.t.g_sigma = dt.take(S);
+        dt.t.logPi = dt.take(S); dt.t.gX = dt.take(S); dt.t.sqerr = dt.take(S);
+        dt.delta = dt.take(S + 1); dt.errpsf = dt.take(S);
+        dt.t.chamb_k = c->trace_i;
         std::vector<double> hd(samples + 1, 0.0);
         for (int i = 1; i <= samples; ++i)                          // delta(i), Guassian.m:55
             hd[i] = prm->d_scale * (std::pow((double)i, -prm->d_exp) / k.dimX);
-        dt.delta = dt.mk<double>(samples + 1, s);
         SBD_CUDA(cudaMemcpyAsync(dt.delta, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice, s));
         SBD_CUDA(cudaStreamSynchronize(s));
         dt.t.delta = dt.delta;
     }
-    dfree(c->allstats);
-    c->allstats = dalloc<double>((size_t)ntot * NSTAT);
+    if (ntot > c->allstats_cap) { dfree(c->allstats); c->allstats = dalloc<double>((size_t)ntot * NSTAT); c->allstats_cap = ntot; }
     double* post = nullptr;
     if (prm->post_mean) {
         if (c->post_batch < nch) { dfree(c->post); c->post = dalloc<double>((size_t)nch * c->npix); c->post_batch = nch; }
@@ -1201,6 +1220,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     }
 
     const double* gstats = nullptr;
+    bool mark_langevin = false;         // set for the last iteration: X is final once its Langevin kernel has run
     auto prox = [&]() {
         PhaseTimer pt(c, 3);
         chambolle(c, c->X, c->P, nch, prm->chambolle_maxiter, true, false);    // zero start: chambolle_prox_TV_stop.m:68-69
@@ -1213,7 +1233,8 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
           const unsigned gx = (unsigned)((c->npix / 2 + 255) / 256);
           k_langevin<<<dim3(gx, nch), 256, 0, s>>>(c->X, c->P, c->Gf, d_noise, post, c->ctl, k.gam, k.lamb, k.sq2gam,
                                                    c->npix, nch, prm->seed, prm->chain_offset, burnIn);
-          LAUNCH_CHECK(c); }
+          LAUNCH_CHECK(c);
+          if (mark_langevin) SBD_CUDA(cudaEventRecord(c->ev_langevin, s)); }
         prox();
         analyse(c, nch);
         if (d_xtrue) {
@@ -1232,13 +1253,17 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     // n iterations of (MYULA step + scalar kernel `mode`).  With use_graph the fixed launch sequence of
     // one iteration (all scalars are device-resident) is captured once and replayed: at small image
     // sizes the iteration is launch-bound and the graph removes most of the per-launch CPU cost.
-    auto run_loop = [&](int n, int mode) {
+    // `mark_last`: record ev_langevin right after the Langevin kernel of the LAST iteration (that iteration is
+    // then launched eagerly), so that the copy of the last samples can overlap its prox / spectral analysis.
+    auto run_loop = [&](int n, int mode, bool mark_last) {
         if (n <= 0) return;
-        const bool graph = prm->use_graph && !c->profile && n >= 4;
+        const bool graph = prm->use_graph && !c->profile && n >= 5;
         if (!graph) {
-            for (int i = 0; i < n; ++i) { myula_step(); scalar(mode); }
+            for (int i = 0; i < n; ++i) { mark_langevin = mark_last && i == n - 1; myula_step(); scalar(mode); }
+            mark_langevin = false;
             return;
         }
+        if (mark_last) n -= 1;                                      // the last one runs eagerly below
         myula_step(); scalar(mode);                                 // first iteration eagerly (sets kernel attributes)
         cudaGraph_t g = nullptr;
         cudaGraphExec_t ge = nullptr;
@@ -1257,6 +1282,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
         SBD_CUDA(cudaGraphInstantiate(&ge, g, 0));
         for (int i = 1; i < n; ++i) SBD_CUDA(cudaGraphLaunch(ge, s));
         c->launches += per_iter * (n - 1);
+        if (mark_last) { mark_langevin = true; myula_step(); scalar(mode); mark_langevin = false; }
         SBD_CUDA(cudaStreamSynchronize(s));
         cudaGraphExecDestroy(ge);
         cudaGraphDestroy(g);
@@ -1265,7 +1291,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     // ---- warm-up (Guassian.m:67-93)
     analyse(c, nch);
     prox();                                                         // :76
-    run_loop(warmup - 1, 1);                                        // :78  for ii = 2:warmupSteps
+    run_loop(warmup - 1, 1, false);                                 // :78  for ii = 2:warmupSteps
     if (out->X_warm)
         SBD_CUDA(cudaMemcpyAsync(out->X_warm, c->X, sizeof(double) * nch * c->npix, cudaMemcpyDeviceToHost, s));
 
@@ -1278,8 +1304,17 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     SBD_CUDA(cudaEventCreate(&evm));
     SBD_CUDA(cudaEventRecord(evm, s));
     const long long launches0 = c->launches;
-    run_loop(samples - 1, 2);                                       // :158  for ii = 2:total_iter
+    const bool overlap_xlast = out->X_last != nullptr && samples >= 2;
+    run_loop(samples - 1, 2, overlap_xlast);                        // :158  for ii = 2:total_iter
     SBD_CUDA(cudaEventRecord(ev1, s));
+    if (overlap_xlast) {
+        // X is final after the last Langevin kernel; what follows in that iteration only reads it.  One copy per
+        // chain on the copy stream, behind the event: it overlaps the last prox and spectral analysis.
+        SBD_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_langevin, 0));
+        for (int ch = 0; ch < nch; ++ch)
+            SBD_CUDA(cudaMemcpyAsync(out->X_last + (size_t)ch * c->npix, c->X + (size_t)ch * c->npix,
+                                     sizeof(double) * c->npix, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
     out->launches_main = c->launches - launches0;
     c->profile = false;
 
@@ -1289,7 +1324,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     const double H0 = now_ms();
     if (dbg_host) { cudaStreamSynchronize(s); fprintf(stderr, "[sbd] impl: loops drained after %.1f ms more\n", now_ms() - H0); }
     const double H1 = now_ms();
-    double* d_errpsf = dt.mk<double>(samples, s);
+    double* d_errpsf = dt.errpsf;
     k_err_psf<<<samples, 256, 0, s>>>(c->model, c->t, c->phi, dt.t.psi0, dt.t.psi1, prm->err_psf_lag,
                                       prm->psi_true[0], prm->psi_true[1], samples, d_errpsf);
     LAUNCH_CHECK(c);
@@ -1310,7 +1345,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     copy_trace(out->err_psf, d_errpsf, samples, s);
     if (out->chambolle_iters)
         SBD_CUDA(cudaMemcpyAsync(out->chambolle_iters, dt.t.chamb_k, sizeof(int) * samples, cudaMemcpyDeviceToHost, s));
-    if (out->X_last)
+    if (out->X_last && !overlap_xlast)
         SBD_CUDA(cudaMemcpyAsync(out->X_last, c->X, sizeof(double) * nch * c->npix, cudaMemcpyDeviceToHost, s));
     if (out->X_mean && post) {
         k_chain_mean<<<(unsigned)((c->npix + 255) / 256), 256, 0, s>>>(post, c->Gf, c->npix, nch);
@@ -1318,6 +1353,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
         SBD_CUDA(cudaMemcpyAsync(out->X_mean, c->Gf, sizeof(double) * c->npix, cudaMemcpyDeviceToHost, s));
     }
     SBD_CUDA(cudaStreamSynchronize(s));
+    if (overlap_xlast) SBD_CUDA(cudaStreamSynchronize(c->copy_stream));
     if (dbg_host) fprintf(stderr, "[sbd] impl: read-back %.1f ms\n", now_ms() - H1);
     float ms = 0.f;
     SBD_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));

@@ -21,7 +21,23 @@ switch model
         P.sigma2_fixed = op.sigma^2; P.err_psf_lag = 0;              % laplace.m:182
 end
 P.prox_lambda = op.lambda;                                           % run_Gaussian_demo.m:191
+% Chambolle options: the reference hard-wires them inside op.proxG (run_Gaussian_demo.m:188-191: 'maxiter',
+% op.chambolleit with the defaults tol = 1e-3, tau = 0.249 of chambolle_prox_TV_stop.m:77-78).  A handle cannot be
+% inspected, so the plain fields are honoured instead (same names as the Python front end, host.make_params).
 P.chambolle_maxiter = 25; P.chambolle_tol = 1e-3; P.chambolle_tau = 0.249;
+if isfield(op, 'chambolleit'), P.chambolle_maxiter = op.chambolleit; end
+if isfield(op, 'chambolle_tol'), P.chambolle_tol = op.chambolle_tol; end
+if isfield(op, 'chambolle_tau'), P.chambolle_tau = op.chambolle_tau; end
+% The closures in op (proxG, gradF, logPi, f, g, grad_*) are NOT called: the engine implements the model they
+% encode.  Say so once, so that an edited closure does not silently go unused.
+hnames = {'proxG', 'gradF', 'logPi', 'f', 'g', 'gradF_sigma'};
+for k = 1:numel(hnames)
+    if isfield(op, hnames{k}) && ~(isfield(op, 'sbd_quiet') && op.sbd_quiet)
+        warning('sbd:handlesIgnored', ['op.' hnames{k} ' (and the other function handles in op) are not called by the ' ...
+                'GPU engine; set op.chambolleit / op.chambolle_tol / op.chambolle_tau or op.sbd_quiet = 1']);
+        break;
+    end
+end
 P.th_init = op.th_init; P.min_th = op.min_th; P.max_th = op.max_th;
 P.psi_init = [0 0]; P.psi_min = [0 0]; P.psi_max = [0 0]; P.psi_fixed = [0 0]; P.psi_true = [0 0]; P.fix_psi = [0 0];
 for k = 1:numel(names)

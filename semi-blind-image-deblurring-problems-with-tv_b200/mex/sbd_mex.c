@@ -127,6 +127,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
                 *py = mxCreateDoubleMatrix(rows, cols, mxREAL);
         if (nrhs > 7 && !mxIsEmpty(prhs[6])) {
             px0 = image(prhs[6], "px", &r2, &c2);
+            if (r2 != rows || c2 != cols) mexErrMsgIdAndTxt("sbd:size", "Wrong size of the dual variables");
             py0 = image(prhs[7], "py", &r2, &c2);
             if (r2 != rows || c2 != cols) mexErrMsgIdAndTxt("sbd:size", "Wrong size of the dual variables");
         }

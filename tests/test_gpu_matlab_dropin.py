@@ -18,13 +18,21 @@ def sc(v):
     return float(np.asarray(v).ravel()[0])
 
 
-@pytest.fixture(scope="module")
-def it():
+@pytest.fixture(scope="module", params=["mex_gateway", "python_bridge"])
+def it(request):
+    """`mex_gateway`: sbd_mex is the REAL mexFunction of mex/sbd_mex.c, linked against libsbd.so and run on the minimal
+    mxArray runtime of tests/mexrt (MATLAB/Octave are absent); `python_bridge`: the ctypes re-implementation."""
     import sbd_b200
     from oracle.mlab.interp import Interp
-    from mex_bridge import make_sbd_mex
     interp = Interp([MATLAB_DIR])
-    interp.builtins["sbd_mex"] = make_sbd_mex(sbd_b200)
+    if request.param == "mex_gateway":
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "tests", "mexrt"))
+        import runtime
+        interp.builtins["sbd_mex"] = runtime.make_sbd_mex_real()
+    else:
+        from mex_bridge import make_sbd_mex
+        interp.builtins["sbd_mex"] = make_sbd_mex(sbd_b200)
     return interp
 
 

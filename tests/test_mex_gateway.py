@@ -46,3 +46,34 @@ def test_wrappers_parse_as_matlab():
     for f in sorted(os.listdir(d)):
         if f.endswith(".m"):
             Parser(tokenize(open(os.path.join(d, f)).read())).parse_file()
+
+
+def test_gateway_executes_on_the_stub_runtime():
+    """mex/sbd_mex.c linked with libsbd.so and tests/mexrt/stub_mx.c: mexFunction really runs.  Without a GPU the
+    commands that need a context must raise through mexErrMsgIdAndTxt with libsbd's own message (no CPU fallback)."""
+    import sys
+    import numpy as np
+    import pytest
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "mexrt"))
+    import __graft_entry__ as g
+    g.build()
+    import runtime
+    with pytest.raises(runtime.MexError) as e:
+        runtime.call_mex("no_such_command")
+    assert e.value.ident == "sbd:usage"
+    with pytest.raises(runtime.MexError) as e:
+        runtime.call_mex(np.ones((2, 2)))                       # first argument must be the command string
+    assert e.value.ident == "sbd:usage"
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(runtime.MexError) as e:
+            runtime.call_mex("tvnorm", np.ones((8, 8)))
+        assert e.value.ident == "sbd:error" and "no CPU fallback" in e.value.msg
+    # value marshalling of the runtime itself (column-major, complex split, struct fields)
+    a = np.arange(6.0).reshape(2, 3)
+    assert np.array_equal(runtime.from_mx(runtime.to_mx(a)), a)
+    z = a + 1j * a[::-1]
+    assert np.array_equal(runtime.from_mx(runtime.to_mx(z)), z)
+    s = runtime.from_mx(runtime.to_mx({"u": 3.0, "v": a}))
+    assert s["u"].item() == 3.0 and np.array_equal(s["v"], a)

@@ -16,6 +16,12 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--per", type=int, default=2, help="chains per rank")
+    ap.add_argument("--samples", type=int, default=30)
+    a = ap.parse_args()
     import torch
     import torch.distributed as dist
     import sbd_b200
@@ -25,15 +31,16 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, per = 128, 2
+    n, per = a.size, a.per
     total = per * world
-    x = np.load(os.path.join(ROOT, "tests", "golden", "cman_u8.npy")).astype(np.float64)[64:64 + n, 64:64 + n]
+    cm = np.load(os.path.join(ROOT, "tests", "golden", "cman_u8.npy")).astype(np.float64)
+    x = cm[64:64 + n, 64:64 + n] if n <= 128 else np.tile(cm, ((n + 255) // 256, (n + 255) // 256))[:n, :n].copy()
     eng = sbd_b200.Engine(n, n, 7, H.MOFFAT, 0.0, total, local)
     Ax = eng.blur(x, (0.4, 3.5), H.OP_A)
     nrm = float(np.linalg.norm(Ax - Ax.mean()))
     sig = lambda b: nrm / np.sqrt(n * n * 10 ** (b / 10))
     y = Ax + sig(30) * np.random.default_rng(2).standard_normal((n, n))
-    op = dict(samples=30, warmup=8, burnIn=20, psf_size=7, min_th=1e-3, max_th=1.0, th_init=0.01,
+    op = dict(samples=a.samples, warmup=8, burnIn=max(2, a.samples * 2 // 3), psf_size=7, min_th=1e-3, max_th=1.0, th_init=0.01,
               alpha_init=1.0, beta_init=10.0, min_alpha=1e-2, max_alpha=1.0, min_beta=0.1, max_beta=10.0,
               alpha=0.4, beta=3.5, fix_alpha=0, fix_beta=0, fix_sigma=0, d_exp=0.8, d_scale=1.0,
               sigma=sig(30), sigma_init=(sig(18) ** 2 + sig(35) ** 2) / 2, sigma_min=sig(18) ** 2, sigma_max=sig(35) ** 2)
