@@ -216,6 +216,31 @@ __device__ __forceinline__ void fft_run(bool active, int tl, double2* __restrict
     }
 }
 
+// Same transform, but the caller consumes the 16 results of the last stage itself: `last(v)` receives the
+// registers of the last stage_load, v[m*R + r] being the result for position jb + r*(N/R), jb = tl + m*N/16.
+template <int N, bool INV, class Src, class Last>
+__device__ __forceinline__ void fft_run_last(bool active, int tl, double2* __restrict__ s, int cs,
+                                             const double2* __restrict__ tw, Src src0, Last last) {
+    using P = FftPlan<N>;
+    double2 v[16];
+    auto smem_src = [&](int p) { return s[fft_pad<N>(p) * cs]; };
+    auto smem_dst = [&](int p, double2 x) { s[fft_pad<N>(p) * cs] = x; };
+    if (active) {
+        stage_load<N, P::R0, 1, INV>(tl, v, src0, tw);
+        stage_store<N, P::R0, 1>(tl, v, smem_dst);
+    }
+    __syncthreads();
+    if constexpr (P::NST == 3) {
+        if (active) stage_load<N, P::R1, P::R0, INV>(tl, v, smem_src, tw);
+        __syncthreads();
+        if (active) stage_store<N, P::R1, P::R0>(tl, v, smem_dst);
+        __syncthreads();
+        if (active) { stage_load<N, P::R2, P::R0 * P::R1, INV>(tl, v, smem_src, tw); last(v); }
+    } else {
+        if (active) { stage_load<N, P::R1, P::R0, INV>(tl, v, smem_src, tw); last(v); }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // half-spectrum addressing (tile-major)
 // ---------------------------------------------------------------------------
@@ -345,7 +370,7 @@ k_rows_inv(const double2* __restrict__ spec, double* __restrict__ out, SpecGeom 
 // dynamic smem = C*fft_line_elems<N>()*16 bytes.  Thread -> (tl, c), c fastest.
 // ---------------------------------------------------------------------------
 enum ColMode {
-    COL_FWD = 0,            // spectrum of y (no PSF work)
+    COL_FWD = 0,            // spectrum of y; SYM: stored PRE-ROTATED, Y' = conj((wk w)^3) Y^ (see k_cols)
     COL_FWD_REDUCE = 1,     // X^ = fft; store; rss, c0, c1 against Y^ with the CURRENT parameters
     COL_MUL_INV = 2,        // G^ = conj(H)(H X^ - Y^) * inv_scale ; inverse fft ; store
     COL_OP = 3,             // fft ; multiply by the selected kernel / (nx*ny) ; inverse fft ; store
@@ -373,6 +398,15 @@ struct ColArgs {
 
 // SYM: psf_size == 7, point-symmetric PSF evaluation (psf_sym3); otherwise the Horner form.  A compile-time
 // switch: with both forms in one kernel the 16-times unrolled epilogue doubles to 160 KB of code.
+//
+// SYM and the phase.  Every kernel of the family is K^ = ph * S with ph = (wk w)^3 of unit modulus, the same for
+// the PSF and its derivatives and independent of the parameters, and S REAL.  The likelihood passes only ever
+// see K^ next to Y^ in |H X^ - Y^|^2, Re conj(D X^)(H X^ - Y^) and conj(H)(H X^ - Y^), all of which are unchanged
+// when Y^ is replaced by Y' = conj(ph) Y^ and every K^ by its real factor:
+//     |sh X^ - Y'|^2,   s_d Re conj(X^)(sh X^ - Y'),   sh (sh X^ - Y').
+// So Y^ is stored pre-rotated (COL_FWD, once per run) and the per-step passes do real multiplications only; the
+// real factors along the 16 bins a thread owns come from psf_seq (psf.cuh).  COL_OP (the A / A' / dif_* operator
+// entry) is the only mode that needs the true phase.
 template <int N, int MODE, bool SYM>
 __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
     extern __shared__ double2 fsm[];
@@ -409,7 +443,7 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
     double2* out = a.out + tile_off;
     const double2* yh = a.yhat + (size_t)tile * N * LC + (size_t)sub * C;
 
-    if (MODE != COL_FWD) {
+    if (MODE != COL_FWD || SYM) {
         for (int e = threadIdx.x; e < C * 3 * a.t; e += blockDim.x) {
             const int j = e % a.t, m = (e / a.t) % 3, c = e / (3 * a.t);
             const int k = min(k0 + c, a.nk - 1);
@@ -435,6 +469,29 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
     if (MODE == COL_MUL_INV) {
         if (active) stage_fetch<N, FftPlan<N>::R0>(tl, raw, [&](int q) { return __ldg(in + (size_t)q * LC + c); });
         __syncthreads();
+        if (SYM && active) {
+            // G^ = sc * sh * (sh X^ - Y'): real factors along the R0 operands of each first-stage butterfly
+            constexpr int R = FftPlan<N>::R0, M = 16 / R, Q = N / R;
+            const double sc = a.ctl->inv_scale;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int jb = tl + m * TL;
+                const PsfSeqK kh = psf_seq_prep(coefS[c][0], psf_seq_w(__ldg(a.tw + jb)));
+                static_for<0, R / 4>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    double sh[4];
+                    psf_seq_eval4<R, r>(kh, sh);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = r + i * (R / 4);
+                        const double2 yv = __ldg(yh + (size_t)(jb + rr * Q) * LC + c);
+                        const double2 v = raw[m * R + rr];
+                        const double t = sh[i] * sc;
+                        raw[m * R + rr] = make_double2(t * fma(sh[i], v.x, -yv.x), t * fma(sh[i], v.y, -yv.y));
+                    }
+                });
+            }
+        }
     }
 
     const int k = k0 + c;
@@ -456,7 +513,7 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
         double2 v;
         if (MODE == COL_MUL_INV) v = raw[nraw++];
         else v = __ldg(in + (size_t)q * LC + c);
-        if (MODE == COL_MUL_INV) {
+        if (MODE == COL_MUL_INV && !SYM) {
             const double2 w = __ldg(a.tw + q);
             const double2 H = kern(0, w);
             const double2 yv = __ldg(yh + (size_t)q * LC + c);
@@ -469,6 +526,10 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
     };
     auto gdst = [&](int q, double2 v) {
         if (!kin) return;
+        if (MODE == COL_FWD && SYM) {                // Y' = conj((wk w)^3) Y^
+            const PsfW3 p = psf_w3(__ldg(a.tw + q));
+            v = cmulc(v, cmul(coefS[c][0][4], p.w3));
+        }
         out[(size_t)q * LC + c] = v;
         if (MODE == COL_FWD_REDUCE) {
             const double2 w = __ldg(a.tw + q);
@@ -477,14 +538,12 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
             const double wt = (k == 0 || 2 * k == a.nxfull) ? 1.0 : 2.0;
             double2 R, T0, T1 = make_double2(0.0, 0.0);
             if (sym) {
-                // the common factor (wk w)^3 of the three kernels is applied to X^ once; what is left of
-                // each kernel is a real number
+                // (only reached when the block epilogue below is not used) Y^ is pre-rotated: real factors only
                 const PsfW3 p = psf_w3(w);
-                const double2 xr = cmul(cmul(coefS[c][0][4], p.w3), v);
                 const double sh = psf_sym3(coefS[c][0], p), s0 = psf_sym3(coefS[c][1], p);
-                R = make_double2(fma(sh, xr.x, -yv.x), fma(sh, xr.y, -yv.y));
-                T0 = make_double2(s0 * xr.x, s0 * xr.y);
-                if (a.npsi > 1) { const double s1 = psf_sym3(coefS[c][2], p); T1 = make_double2(s1 * xr.x, s1 * xr.y); }
+                R = make_double2(fma(sh, v.x, -yv.x), fma(sh, v.y, -yv.y));
+                T0 = make_double2(s0 * v.x, s0 * v.y);
+                if (a.npsi > 1) { const double s1 = psf_sym3(coefS[c][2], p); T1 = make_double2(s1 * v.x, s1 * v.y); }
             } else {
                 R = csub(cmul(psf_horner(coefS[c][0], a.t, w), v), yv);
                 T0 = cmul(psf_horner(coefS[c][1], a.t, w), v);
@@ -501,7 +560,8 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
         auto sdst = [&](int q, double2 v) {
             if (MODE == COL_FILTER) {
                 const double2 w = __ldg(a.tw + q);
-                const double2 H = kern(0, w);
+                // SYM: Y^ is stored pre-rotated, |Y^ - H X^| = |Y' - sh X^| with the real factor sh of H
+                const double2 H = sym ? make_double2(psf_sym3(coefS[c][0], psf_w3(w)), 0.0) : kern(0, w);
                 const double F = 1.0 / ((H.x * H.x + H.y * H.y) + a.mu);       // filter_FFT, demo:224
                 const double2 X = make_double2(v.x * F, v.y * F);
                 if (kin) {
@@ -565,6 +625,46 @@ __global__ void __launch_bounds__(512) k_cols(const ColArgs a) {
         }
     } else if (MODE == COL_MUL_INV) {
         fft_run<N, true, false>(active, tl, line, C, a.tw, gsrc, gdst);
+    } else if (MODE == COL_FWD_REDUCE && SYM) {
+        // forward transform whose last stage is followed, butterfly by butterfly, by the likelihood sums
+        //   rss += |sh X^ - Y'|^2,  c_d += s_d Re conj(X^)(sh X^ - Y')      (Hermitian weight applied once at the end)
+        using P = FftPlan<N>;
+        constexpr int RL = (P::NST == 3) ? P::R2 : P::R1, NSL = N / RL, ML = 16 / RL;
+        auto last = [&](const double2 (&v)[16]) {
+#pragma unroll
+            for (int m = 0; m < ML; ++m) {
+                const int jb = tl + m * TL;
+                const PsfSeqW w = psf_seq_w(__ldg(a.tw + jb));
+                const PsfSeqK kh = psf_seq_prep(coefS[c][0], w), kd0 = psf_seq_prep(coefS[c][1], w);
+                PsfSeqK kd1 = kd0;
+                if (a.npsi > 1) kd1 = psf_seq_prep(coefS[c][2], w);
+                static_for<0, RL / 4>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    double sh[4], s0[4], s1[4];
+                    psf_seq_eval4<RL, r>(kh, sh);
+                    psf_seq_eval4<RL, r>(kd0, s0);
+                    if (a.npsi > 1) psf_seq_eval4<RL, r>(kd1, s1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = r + i * (RL / 4);
+                        const size_t o = (size_t)(jb + rr * NSL) * LC + c;
+                        const double2 x = v[m * RL + rr];
+                        if (kin) {
+                            const double2 yv = __ldg(yh + o);
+                            out[o] = x;
+                            const double rx = fma(sh[i], x.x, -yv.x), ry = fma(sh[i], x.y, -yv.y);
+                            acc[0] = fma(rx, rx, fma(ry, ry, acc[0]));
+                            const double d = fma(x.x, rx, x.y * ry);            // Re conj(X^) R'
+                            acc[1] = fma(s0[i], d, acc[1]);
+                            if (a.npsi > 1) acc[2] = fma(s1[i], d, acc[2]);
+                        }
+                    }
+                });
+            }
+        };
+        fft_run_last<N, false>(active, tl, line, C, a.tw, gsrc, last);
+        const double wt = (k == 0 || 2 * k == a.nxfull) ? 1.0 : 2.0;    // Hermitian weights of the half spectrum
+        acc[0] *= wt; acc[1] *= wt; acc[2] *= wt;
     } else {
         fft_run<N, false, false>(active, tl, line, C, a.tw, gsrc, gdst);
     }

@@ -8,6 +8,7 @@
 //   utils/laplace_psf.m:1-15,  utils/sum_lap_psf.m:1-28,   utils/diff_laplace_b.m:1-19
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace sbd {
 
@@ -133,6 +134,72 @@ __device__ __forceinline__ double2 psf_sym3_coef(const double2* __restrict__ c, 
     if (m == 0) return make_double2(cmul(wk3c, c[3]).x, 0.0);
     const double2 hi = cmul(wk3c, c[3 + m]), lo = cmul(wk3c, c[3 - m]);
     return make_double2(hi.x + lo.x, -(hi.y - lo.y));
+}
+
+// ---------------------------------------------------------------------------
+// The real factor S along the R outputs of one radix-R butterfly.
+// A thread of the column pass owns, per butterfly, the bins q_r = jb + r*N/R, r = 0..R-1 (the outputs of the last
+// forward stage, or the operands of the first inverse stage), i.e. w_(q_r) = w_jb * W_R^r with W_R = e^(-2 pi i / R).
+// With A_j = (e_j - i f_j) * w_jb^j = (x_j, y_j):
+//     S_r = e0 + sum_{j=1..3} Re[A_j W_R^(j r)] = e0 + sum_j (x_j cos(2 pi j r / R) + y_j sin(2 pi j r / R)),
+// whose angles are compile-time constants: no per-element w^2, w^3, no table look-ups.  Half-turn symmetry
+// (j r -> j (r + R/2) flips the sign of the odd j) and the quarter-turn symmetry of the j = 2 term give
+//     S_r = P_r + Q_r,  S_(r+R/2) = P_r - Q_r,  P_r = e0 + T2_r,  P_(r+R/4) = e0 - T2_r,  Q_r = T1_r + T3_r,
+// about 60 fp64 operations for the 16 values of a radix-16 butterfly instead of 16 * (6 + the per-element powers
+// of w).  The values are produced four at a time (r, r+R/4, r+R/2, r+3R/4) so that no array of R values is live.
+// ---------------------------------------------------------------------------
+template <int N16>
+__device__ __forceinline__ double rot_re(double x, double y) {      // x cos(2 pi n/16) + y sin(2 pi n/16)
+    constexpr int n = ((N16 % 16) + 16) % 16;
+    constexpr double H = 0.70710678118654752440, C1 = 0.92387953251128675613, S1 = 0.38268343236508977173;
+    if constexpr (n == 0) return x;
+    else if constexpr (n == 4) return y;
+    else if constexpr (n == 8) return -x;
+    else if constexpr (n == 12) return -y;
+    else if constexpr (n == 2) return (x + y) * H;
+    else if constexpr (n == 6) return (y - x) * H;
+    else if constexpr (n == 10) return -((x + y) * H);
+    else if constexpr (n == 14) return (x - y) * H;
+    else {
+        constexpr double c = (n == 1 || n == 15) ? C1 : (n == 3 || n == 13) ? S1 : (n == 5 || n == 11) ? -S1 : -C1;
+        constexpr double sn = (n == 1 || n == 7) ? S1 : (n == 3 || n == 5) ? C1 : (n == 9 || n == 15) ? -S1 : -C1;
+        return fma(x, c, y * sn);
+    }
+}
+struct PsfSeqW { double2 w1, w2, w3; };      // w_jb, w_jb^2, w_jb^3
+__device__ __forceinline__ PsfSeqW psf_seq_w(double2 w) {
+    PsfSeqW p; p.w1 = w; p.w2 = cmul(w, w); p.w3 = cmul(p.w2, w);
+    return p;
+}
+struct PsfSeqK { double e0, x[3], y[3]; };   // one kernel along one butterfly: e0 and A_j = (x_j, y_j)
+// b = coefS[c][m] (b[0] = (e0, 0), b[j] = (e_j, f_j))
+__device__ __forceinline__ PsfSeqK psf_seq_prep(const double2* __restrict__ b, const PsfSeqW& w) {
+    PsfSeqK k;
+    k.e0 = b[0].x;
+    // (e - i f)(a + i b) = (e a + f b) + i (e b - f a)
+    k.x[0] = fma(b[1].x, w.w1.x, b[1].y * w.w1.y); k.y[0] = fma(b[1].x, w.w1.y, -b[1].y * w.w1.x);
+    k.x[1] = fma(b[2].x, w.w2.x, b[2].y * w.w2.y); k.y[1] = fma(b[2].x, w.w2.y, -b[2].y * w.w2.x);
+    k.x[2] = fma(b[3].x, w.w3.x, b[3].y * w.w3.y); k.y[2] = fma(b[3].x, w.w3.y, -b[3].y * w.w3.x);
+    return k;
+}
+// the four values S[i] at r + i*R/4, i = 0..3 (r < R/4): they share T2 and the two Q sums
+template <int R, int r>
+__device__ __forceinline__ void psf_seq_eval4(const PsfSeqK& k, double (&S)[4]) {
+    static_assert(R == 4 || R == 8 || R == 16, "radix");
+    static_assert(r >= 0 && r < R / 4, "r");
+    constexpr int u = 16 / R, r1 = r + R / 4;
+    const double T2 = rot_re<2 * r * u>(k.x[1], k.y[1]);
+    const double P0 = k.e0 + T2, P1 = k.e0 - T2;
+    const double Q0 = rot_re<1 * r * u>(k.x[0], k.y[0]) + rot_re<3 * r * u>(k.x[2], k.y[2]);
+    const double Q1 = rot_re<1 * r1 * u>(k.x[0], k.y[0]) + rot_re<3 * r1 * u>(k.x[2], k.y[2]);
+    S[0] = P0 + Q0; S[1] = P1 + Q1; S[2] = P0 - Q0; S[3] = P1 - Q1;
+}
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
 }
 
 // Full rows x cols spectrum for sbd_psf_spectrum (API / parity path only).

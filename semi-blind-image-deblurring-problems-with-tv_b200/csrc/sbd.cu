@@ -9,6 +9,7 @@
 #include "tv.cuh"
 #include "tv_multi.cuh"
 #include "fft.cuh"
+#include "fft2.cuh"
 #include "sapg.cuh"
 
 #include <dlfcn.h>
@@ -82,6 +83,10 @@ struct sbd_ctx {
     int rowsLP = 1, rowsT = 32, colsC = 2, colsLogC = 1, colsT = 32, ntiles = 1;
     int colsKC = 2, colsLogKC = 1;     // columns per block of the column pass (<= colsC, the layout tile width)
     size_t rows_smem = 0, cols_smem = 0;
+    // v2 passes (fft2.cuh): column-contiguous spectrum, bulk / tensor copies.  Tensor maps of the spectra buffers
+    // the rows passes write (S1, Y^) or read (S2, S1), built when the buffers are allocated.
+    bool v2 = false;
+    CUtensorMap tm_S1, tm_S2, tm_yhat;
     int geom_batch = -1;
     // launch-geometry overrides (sbd_set_option; -1 = automatic).  Seeded from the SBD_* environment at sbd_create.
     int opt_chamb_seg = -1, opt_chamb_T = -1, opt_tv_seg = -1, opt_chamb_emit = -1, opt_chamb_plan33 = -1;
@@ -175,6 +180,36 @@ void free_ws(sbd_ctx* c) {
     c->ws_batch = 0;
 }
 
+// 3-D tensor map of a spectrum buffer as doubles {2*ny (q, re/im), nk (k), batch}; box = 2 complex x 256 bins
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+CUtensorMap make_spec_tmap(sbd_ctx* c, double2* base, int batch) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        SBD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        SBD_REQUIRE(fn && qr == cudaDriverEntryPointSuccess, SBD_E_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+        encode = (EncodeTiledFn)fn;
+    }
+    CUtensorMap tm;
+    const cuuint64_t gdim[3] = {(cuuint64_t)2 * c->ny, (cuuint64_t)c->nk, (cuuint64_t)batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)c->ny * 16, (cuuint64_t)c->spec_elems * 16};
+    const cuuint32_t box[3] = {4, (cuuint32_t)TMA_KBOX, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error{SBD_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
+    return tm;
+}
+const CUtensorMap& spec_tmap(sbd_ctx* c, const double2* buf) {
+    if (buf == c->S1) return c->tm_S1;
+    if (buf == c->S2) return c->tm_S2;
+    if (buf == c->yhat) return c->tm_yhat;
+    throw Error{SBD_E_INVALID, "rows pass: spectrum buffer without a tensor map"};
+}
+
 // choose launch geometry for a batch of `batch` images
 void set_geometry(sbd_ctx* c, int batch_local) {
     const int batch = std::max(batch_local, c->geom_total);
@@ -231,6 +266,7 @@ void ensure_ws(sbd_ctx* c, int batch) {
     if (c->pow2) {
         c->S1 = dalloc<double2>((size_t)batch * c->spec_elems);
         c->S2 = dalloc<double2>((size_t)batch * c->spec_elems);
+        if (c->v2) { c->tm_S1 = make_spec_tmap(c, c->S1, batch); c->tm_S2 = make_spec_tmap(c, c->S2, batch); }
     }
     c->chst = dalloc<ChambState>(batch);
     c->cnt_tv = dalloc<unsigned int>(batch); c->cnt_col = dalloc<unsigned int>(batch); c->cnt_sq = dalloc<unsigned int>(batch);
@@ -420,7 +456,23 @@ SpecGeom spec_geom(const sbd_ctx* c) {
     return g;
 }
 
+#define SBD_FFT2_SIZES(X) X(1024) X(2048) X(4096)
+
 void rows_fwd(sbd_ctx* c, const double* x, double2* spec, int batch) {
+    if (c->v2) {
+        const size_t smem2 = (size_t)c->nx * 16;
+        dim3 g2(c->ny / 2, batch);
+        const CUtensorMap& tm = spec_tmap(c, spec);
+        switch (c->nx) {
+#define X(N) case N: set_smem(c, k_rows2_fwd<N>, smem2); \
+            k_rows2_fwd<N><<<g2, N / 16, smem2, c->stream>>>(x, spec, tm, c->ny, c->npix, c->spec_elems, c->tw_nx); break;
+            SBD_FFT2_SIZES(X)
+#undef X
+            default: throw Error{SBD_E_UNSUPPORTED, "rows_fwd (v2): unsupported size"};
+        }
+        LAUNCH_CHECK(c);
+        return;
+    }
     const size_t smem = c->rows_smem;
     dim3 g(c->ny / 2 / c->rowsLP, batch);
     const SpecGeom sg = spec_geom(c);
@@ -436,6 +488,20 @@ void rows_fwd(sbd_ctx* c, const double* x, double2* spec, int batch) {
 }
 
 void rows_inv(sbd_ctx* c, const double2* spec, double* out, int batch) {
+    if (c->v2) {
+        const size_t smem2 = (size_t)c->nx * 16;
+        dim3 g2(c->ny / 2, batch);
+        const CUtensorMap& tm = spec_tmap(c, spec);
+        switch (c->nx) {
+#define X(N) case N: set_smem(c, k_rows2_inv<N>, smem2); \
+            k_rows2_inv<N><<<g2, N / 16, smem2, c->stream>>>(spec, out, tm, c->ny, c->npix, c->spec_elems, c->tw_nx); break;
+            SBD_FFT2_SIZES(X)
+#undef X
+            default: throw Error{SBD_E_UNSUPPORTED, "rows_inv (v2): unsupported size"};
+        }
+        LAUNCH_CHECK(c);
+        return;
+    }
     const size_t smem = c->rows_smem;
     dim3 g(c->ny / 2 / c->rowsLP, batch);
     const SpecGeom sg = spec_geom(c);
@@ -459,6 +525,19 @@ void cols(sbd_ctx* c, const double2* in, double2* out, int batch, int opsel = 0)
     a.nsub = c->colsC / c->colsKC; a.ntiles = c->ntiles; a.opsel = opsel;
     a.opscale = 1.0 / ((double)c->nx * (double)c->ny);
     a.mu = c->salsa_mu;
+    if (c->v2) {
+        const size_t smem2 = (size_t)c->ny * 16;
+        dim3 g2(batch, c->nk);
+        a.pf = 0;
+        switch (c->ny) {
+#define X(N) case N: set_smem(c, k_cols2<N, MODE>, smem2); k_cols2<N, MODE><<<g2, N / 16, smem2, c->stream>>>(a); break;
+            SBD_FFT2_SIZES(X)
+#undef X
+            default: throw Error{SBD_E_UNSUPPORTED, "cols (v2): unsupported size"};
+        }
+        LAUNCH_CHECK(c);
+        return;
+    }
     const size_t smem = c->cols_smem;
     dim3 g(batch, c->ntiles * (c->colsC / c->colsKC));
     switch (c->ny) {
@@ -588,12 +667,16 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
         if (c->pow2) {
             // column pass: C bins per block (tile-major half spectrum); padded line of ny elements
             const size_t le_y = (size_t)cols + cols / (cols >= 1024 || cols == 256 || cols == 128 ? 16 : (cols == 16 ? 4 : 8));
+            // large images with the 7 x 7 PSF of the reference demos: the bulk / tensor-copy passes of fft2.cuh, which
+            // use the column-contiguous layout (tile width 1).  SBD_FFT_V2=0 keeps the tiled passes of fft.cuh.
+            c->v2 = rows >= 1024 && cols >= 1024 && psf_size == 7 && !(getenv("SBD_FFT_V2") && atoi(getenv("SBD_FFT_V2")) == 0);
             int C = 8;
             const size_t cap = (cols >= 2048) ? 144 * 1024 : 74 * 1024;
             while (C > 1 && (size_t)C * le_y * 16 > cap) C /= 2;
+            if (c->v2) C = 1;
             if (const char* e = getenv("SBD_COLS_C")) {
                 const int v = atoi(e);
-                if (v == 1 || v == 2 || v == 4 || v == 8) C = v;
+                if ((v == 1 || v == 2 || v == 4 || v == 8) && !c->v2) C = v;
             }
             c->colsC = C;
             c->colsLogC = (C == 8) ? 3 : (C == 4) ? 2 : (C == 2) ? 1 : 0;
@@ -638,6 +721,7 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
             make_twiddles(cols, c->tw_ny, c->stream);
             c->coef = dalloc<double2>((size_t)3 * rows * MAXT);
             c->yhat = dalloc<double2>(c->spec_elems);
+            if (c->v2) c->tm_yhat = make_spec_tmap(c, c->yhat, 1);
         }
         SBD_CUDA(cudaStreamSynchronize(c->stream));
         *out = c;

@@ -1,16 +1,21 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -x -q > gpurun_out/r02_t3.log 2>&1; tail -8 gpurun_out/r02_t3.log
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-size-sweep --no-extras > gpurun_out/r02_b3.json 2> gpurun_out/r02_b3.err; tail -3 gpurun_out/r02_b3.err
-python - <<P
-import json
-for l in open('gpurun_out/r02_b3.json'):
-    if l.startswith('{'):
-        d=json.loads(l); print(d['value'], d['ms_per_step'], d['e2e']); print(d['roofline']['issue_frac'], d['clocks'])
-P
-SBD_TRACE_HOST=1 python bench.py --steps 20 --warmup 3 --chains-per-gpu 8 --no-cpu-baseline --no-size-sweep --no-extras 2>&1 | python -c "
+python -m pytest tests -m gpu -x -q > gpurun_out/r02_t5.log 2>&1; tail -15 gpurun_out/r02_t5.log
+CMD="python bench.py --steps 6 --warmup 3 --chains-per-gpu 8 --no-cpu-baseline --no-size-sweep --no-extras"
+$CMD 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print(d['value'], d['ms_per_step'], d['e2e'])
-    else: print(l.rstrip()[:200])
+        d=json.loads(l); print(d['value'], d['ms_per_step'], d['e2e']['value']); print(d['fused_step']['phase_ms_per_step'])
+    else: print(l.rstrip()[:300])
 "
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_cols|k_rows' -s 20 -c 30 --csv --log-file gpurun_out/r02_l6.csv $CMD > /dev/null 2>&1
+python - <<P
+import csv,collections
+rows=[r for r in csv.reader(open('gpurun_out/r02_l6.csv')) if len(r)>10]
+h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value'); 
+d=collections.defaultdict(list)
+for r in rows[1:]:
+    try: d[r[ki][:60]].append(float(r[vi].replace(',','')))
+    except: pass
+for k,v in d.items(): print(k, len(v), round(sum(v)/len(v)/1e3,1),'us', 'max',round(max(v)/1e3,1))
+P
