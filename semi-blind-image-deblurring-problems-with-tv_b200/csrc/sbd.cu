@@ -237,6 +237,10 @@ void set_geometry(sbd_ctx* c, int batch_local) {
         // parallelism (256^2, one chain: 4-row segments are 10 % faster than 8-row ones)
         while (sg > 8 && (long long)c->cm_gx * ((ny + sg - 1) / sg) * batch < 6 * 148) sg /= 2;
         if (sg == 8 && (long long)c->cm_gx * ((ny + 7) / 8) * batch < 2 * 148) sg = 4;      // less than two blocks per SM
+        // very large batches (64 chains at 4096^2): longer segments cut the share of the vertical halo rows; only while
+        // the grid still has >= 20 waves of 3 blocks per SM, so that the tail wave stays negligible (4096^2 x 64 chains:
+        // 80.9 -> 78.2 ms per prox step from 128 to 512 rows)
+        while (sg >= 128 && sg < 512 && (long long)c->cm_gx * ((ny + 2 * sg - 1) / (2 * sg)) * batch >= 20LL * 3 * 148) sg *= 2;
         if (c->opt_chamb_seg > 0) sg = c->opt_chamb_seg;
         if (c->opt_chamb_emit >= 0) c->cm_emit = c->opt_chamb_emit != 0;
         if (c->opt_chamb_plan33 >= 0) c->cm_plan33 = c->opt_chamb_plan33 != 0;

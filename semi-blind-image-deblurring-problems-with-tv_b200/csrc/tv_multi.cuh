@@ -72,32 +72,92 @@ __device__ __forceinline__ double seed_with_low_of(double seed, double dead) {
 // for one (tools/fp64_microbench.cu, MIX lines), so the kernel is issue-bound and every instruction
 // counts: the square root / reciprocal refinement is written with the fewest operations that reach
 // ~1 ulp (derivation above).
+// Variants of the level-step arithmetic, A/B-measured with tools/proto/chamb_bench.cu on B200 (4096^2 x 8 chains,
+// 128-row segments, ms per 4-level launch; gpurun_out/r02_chamb_ab*.log):
+//   baseline (integer clamp in front of the rsqrt seed, seed of 1/d from the refined d)        1.532
+//   SBD_CM_BIAS   1e-300 folded into the first square instead of the clamp (-16 integer ops)   1.445   <- default
+//   SBD_CM_REUSE  p - (tau/d)(|grad u| p - grad u), reusing the err terms (-16 fp64 ops)       1.657 (1.636 with BIAS)
+//   SBD_CM_EARLYD reciprocal seed from the unrefined root (+16 fp64, shorter dependency chain) 1.489 (with BIAS)
+//   SBD_CM_OPX0   numerators multiplied by the seed beside the residual (+16 fp64)             1.510 (with BIAS)
+// i.e. the loop follows its instruction count (EARLYD / OPX0 shorten the chain and lose), except where ptxas
+// answers a shorter source with more register moves (REUSE: 108 -> 127 MOVs per trip).
+#ifndef SBD_CM_BIAS
+#define SBD_CM_BIAS 1
+#endif
+#ifndef SBD_CM_REUSE
+#define SBD_CM_REUSE 0
+#endif
+#ifndef SBD_CM_EARLYD
+#define SBD_CM_EARLYD 0
+#endif
+#ifndef SBD_CM_OPX0
+#define SBD_CM_OPX0 0
+#endif
 template <class Lv>
 __device__ __forceinline__ void cm_core(const double (&upx)[2], const double (&un)[2], const Lv& h, double tau,
                                         double (&opx)[2], double (&opy)[2], double (&ex)[2], double (&ey)[2]) {
     double upy[2], s2[2], y[2], g[2], rs[2], r[2], t[2], d[2], ee[2];
+    const double mtau = -tau;
 #define CM_V _Pragma("unroll") for (int v = 0; v < 2; ++v)
     CM_V upy[v] = un[v] - h.u[v];
     double sq[2];
+    // + 1e-300: |grad u|^2 = 0 (flat areas) stays a normal number for the MUFU seed (a * y is then 1e-150 instead of
+    // exactly 0, which changes nothing that is representable: d = 1, p unchanged, err += 1e-300 |p|^2); for any
+    // other value the bias is below half an ulp.  It replaces an integer clamp of the seed's high word.
+#if SBD_CM_BIAS
+    CM_V sq[v] = fma(upy[v], upy[v], 1e-300);
+    CM_V s2[v] = fma(upx[v], upx[v], sq[v]);
+    CM_V y[v] = seed_with_low_of(fast_rsqrt_seed(s2[v]), sq[v]);
+#else
     CM_V sq[v] = upy[v] * upy[v];
     CM_V s2[v] = fma(upx[v], upx[v], sq[v]);
     CM_V y[v] = seed_with_low_of(fast_rsqrt_seed_nz(s2[v]), sq[v]);
+#endif
     CM_V g[v] = s2[v] * y[v];
+#if SBD_CM_EARLYD
+    // reciprocal seed from the UNREFINED root (relative error 2^-23, the same as the seed's own): the MUFU latency
+    // runs under the refinement of the root instead of behind it; the residual below uses the refined d
+    double d0[2];
+    CM_V d0[v] = fma(tau, g[v], 1.0);
+    CM_V rs[v] = seed_with_low_of(fast_rcp_seed(d0[v]), sq[v]);
+#endif
     CM_V r[v] = fma(-g[v], y[v], 1.0);
     CM_V t[v] = fma(r[v], 0.375, 0.5);
     CM_V t[v] = r[v] * t[v];                                                 // r + 1.5 r^2
     CM_V g[v] = fma(g[v], t[v], g[v]);                                       // :127
     CM_V d[v] = fma(tau, g[v], 1.0);
+#if !SBD_CM_EARLYD
     CM_V rs[v] = seed_with_low_of(fast_rcp_seed(d[v]), t[v]);                                        // seed from the final d: no early estimate to compute
-    CM_V ex[v] = fma(g[v], h.px[v], -upx[v]);
+#endif
+    CM_V ex[v] = fma(g[v], h.px[v], -upx[v]);                                // :128
     CM_V ey[v] = fma(g[v], h.py[v], -upy[v]);
     CM_V ee[v] = fma(-d[v], rs[v], 1.0);
+#if SBD_CM_REUSE
+    CM_V ee[v] = fma(ee[v], ee[v], ee[v]);
+    CM_V rs[v] = fma(rs[v], ee[v], rs[v]);                                   // 1 / (1 + tau |grad u|)
+    // :129-130  (p + tau grad u) / d  =  p - (tau / d) (|grad u| p - grad u): the err terms are reused, one fma each
+    CM_V rs[v] = rs[v] * mtau;
+    CM_V opx[v] = fma(rs[v], ex[v], h.px[v]);
+    CM_V opy[v] = fma(rs[v], ey[v], h.py[v]);
+#elif SBD_CM_OPX0
+    // (p + tau grad u) * rs0 * (1 + e + e^2): the product with the seed runs beside the residual, one fma closes
+    CM_V opx[v] = fma(tau, upx[v], h.px[v]);
+    CM_V opy[v] = fma(tau, upy[v], h.py[v]);
+    CM_V opx[v] = opx[v] * rs[v];
+    CM_V opy[v] = opy[v] * rs[v];
+    CM_V ee[v] = fma(ee[v], ee[v], ee[v]);
+    CM_V opx[v] = fma(opx[v], ee[v], opx[v]);                                // :129
+    CM_V opy[v] = fma(opy[v], ee[v], opy[v]);                                // :130
+    (void)mtau;
+#else
     CM_V opx[v] = fma(tau, upx[v], h.px[v]);
     CM_V opy[v] = fma(tau, upy[v], h.py[v]);
     CM_V ee[v] = fma(ee[v], ee[v], ee[v]);
     CM_V rs[v] = fma(rs[v], ee[v], rs[v]);
     CM_V opx[v] = opx[v] * rs[v];                                            // :129
     CM_V opy[v] = opy[v] * rs[v];                                            // :130
+    (void)mtau;
+#endif
 #undef CM_V
 }
 
