@@ -66,6 +66,11 @@ __device__ __forceinline__ void tma_store_commit_wait() {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int TMA_KBOX = 256;       // rows (bins k) per box of the rows-pass tensor copies; box = 256 x 2 complex
+// Slab [k][2] of the rows passes as the TMA lays it out with CU_TENSOR_MAP_SWIZZLE_32B: the two 16-byte halves of
+// row k are exchanged when bit 7 of the row's byte offset is set, i.e. slot(k, w) = 2k + (w ^ ((k >> 2) & 1)).
+// With it eight consecutive k (one shared-memory phase of a 16-byte access) hit eight different bank groups
+// (plain [k][2]: lanes i and i+4 collide, two wavefronts per phase).
+__device__ __forceinline__ int slab(int k, int w) { return 2 * k + (w ^ ((k >> 2) & 1)); }
 
 // ---------------------------------------------------------------------------
 // rows pass, forward.  grid = (ny/2, batch), block = N/16, dynamic smem = N*16 bytes (+ static)
@@ -75,7 +80,7 @@ template <int N>
 __global__ void __launch_bounds__(N / 16, (N == 4096) ? 3 : 1)
 k_rows2_fwd(const double* __restrict__ x, double2* __restrict__ spec, const __grid_constant__ CUtensorMap tm, int ny,
             size_t img_stride, size_t spec_stride, const double2* __restrict__ tw) {
-    extern __shared__ __align__(128) double2 buf[];
+    extern __shared__ __align__(1024) double2 buf[];
     using P = FftPlan<N>;
     static_assert(P::NST == 3 && P::R0 == 16, "v2 passes: 1024 <= N <= 4096");
     constexpr int TL = N / 16;
@@ -113,8 +118,8 @@ k_rows2_fwd(const double* __restrict__ x, double2* __restrict__ spec, const __gr
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = tl + j * TL;
-        buf[2 * k] = make_double2(0.5 * (zk[j].x + zm[j].x), 0.5 * (zk[j].y - zm[j].y));
-        buf[2 * k + 1] = make_double2(0.5 * (zk[j].y + zm[j].y), 0.5 * (zm[j].x - zk[j].x));
+        buf[slab(k, 0)] = make_double2(0.5 * (zk[j].x + zm[j].x), 0.5 * (zk[j].y - zm[j].y));
+        buf[slab(k, 1)] = make_double2(0.5 * (zk[j].y + zm[j].y), 0.5 * (zm[j].x - zk[j].x));
     }
     fence_async_smem();
     __syncthreads();
@@ -137,7 +142,7 @@ template <int N>
 __global__ void __launch_bounds__(N / 16, (N == 4096) ? 3 : 1)
 k_rows2_inv(const double2* __restrict__ spec, double* __restrict__ out, const __grid_constant__ CUtensorMap tm, int ny,
             size_t img_stride, size_t spec_stride, const double2* __restrict__ tw) {
-    extern __shared__ __align__(128) double2 buf[];
+    extern __shared__ __align__(1024) double2 buf[];
     __shared__ __align__(8) unsigned long long mbar;
     using P = FftPlan<N>;
     static_assert(P::NST == 3 && P::R0 == 16, "v2 passes: 1024 <= N <= 4096");
@@ -161,8 +166,8 @@ k_rows2_inv(const double2* __restrict__ spec, double* __restrict__ out, const __
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = tl + j * TL;
-        A[j] = buf[2 * k];
-        B[j] = buf[2 * k + 1];
+        A[j] = buf[slab(k, 0)];
+        B[j] = buf[slab(k, 1)];
     }
     __syncthreads();
 #pragma unroll
@@ -201,7 +206,7 @@ k_rows2_inv(const double2* __restrict__ spec, double* __restrict__ out, const __
 // columns per SM (2 x 256 threads x 128 registers), not three; the third block's worth of shared memory stays free.
 template <int N, int MODE>
 __global__ void __launch_bounds__(N / 16, (N == 4096) ? 2 : 1) k_cols2(const ColArgs a) {
-    extern __shared__ __align__(128) double2 buf[];
+    extern __shared__ __align__(1024) double2 buf[];
     __shared__ double2 coefS[3][MAXT];
     __shared__ double redS[3 * 32];
     __shared__ __align__(8) unsigned long long mbar;
@@ -219,6 +224,7 @@ __global__ void __launch_bounds__(N / 16, (N == 4096) ? 2 : 1) k_cols2(const Col
         bulk_g2s(buf, in, (uint32_t)N * 16u, &mbar);
     }
     // the batch shares Y': the first image's block pulls the column of the NEXT bin into L2 ahead of its use
+    // (measured: asking for the block's OWN Y' column in L1 here instead makes the pass 8 % slower)
     if (img == 0 && k + 1 < a.nk && (MODE == COL_MUL_INV || MODE == COL_FWD_REDUCE || MODE == COL_FILTER))
         l2_prefetch_span(a.yhat + (size_t)(k + 1) * N, (size_t)N * sizeof(double2));
     for (int e = tl; e < 3 * 7; e += TL) {                            // point-symmetric coefficients of this bin
@@ -280,8 +286,25 @@ __global__ void __launch_bounds__(N / 16, (N == 4096) ? 2 : 1) k_cols2(const Col
     __syncthreads();
     stage_store<N, P::R1, R0>(tl, v, sdst);
     __syncthreads();
-    stage_load<N, P::R2, R0 * P::R1, INV1>(tl, v, ssrc, a.tw);
     constexpr int RL = P::R2, NSL = N / RL, ML = 16 / RL;
+    if (MODE == COL_FWD_REDUCE) {
+        // the operands of the last stage go to registers, which frees the buffer: the Y' column of this bin is
+        // bulk-copied into it while the last twiddles and butterflies run, and the likelihood sums then read Y'
+        // from shared memory (16 dependent global loads per thread at the very end of the block were the
+        // top stall of this pass: ncu long_scoreboard 4.4 warps per issue cycle)
+        stage_fetch<N, RL>(tl, raw, ssrc);
+        fence_async_smem();                          // order this thread's earlier generic accesses before the async write
+        __syncthreads();
+        if (tl == 0) {
+            mbar_expect_tx(&mbar, (uint32_t)N * 16u);
+            bulk_g2s(buf, yh, (uint32_t)N * 16u, &mbar);
+        }
+        nraw = 0;
+        stage_load<N, RL, R0 * P::R1, INV1>(tl, v, rsrc, a.tw);
+        mbar_wait(&mbar, 1);
+    } else {
+        stage_load<N, RL, R0 * P::R1, INV1>(tl, v, ssrc, a.tw);
+    }
 
     if (MODE == COL_MUL_INV) {
         stage_store<N, RL, NSL>(tl, v, [&](int q, double2 z) { out[q] = z; });
@@ -311,7 +334,7 @@ __global__ void __launch_bounds__(N / 16, (N == 4096) ? 2 : 1) k_cols2(const Col
                     const int rr = r + i * (RL / 4);
                     const int q = jb + rr * NSL;
                     const double2 x = v[m * RL + rr];
-                    const double2 yv = __ldg(yh + q);
+                    const double2 yv = buf[q];                              // Y' column, natural order
                     out[q] = x;
                     const double rx = fma(sh[i], x.x, -yv.x), ry = fma(sh[i], x.y, -yv.y);
                     acc[0] = fma(rx, rx, fma(ry, ry, acc[0]));

@@ -198,8 +198,10 @@ CUtensorMap make_spec_tmap(sbd_ctx* c, double2* base, int batch) {
     const cuuint64_t gstr[2] = {(cuuint64_t)c->ny * 16, (cuuint64_t)c->spec_elems * 16};
     const cuuint32_t box[3] = {4, (cuuint32_t)TMA_KBOX, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
+    // SWIZZLE_32B: the shared-memory side of a box row (32 bytes) is stored with its halves exchanged in every other
+    // group of four rows - the bank-conflict-free slab layout of fft2.cuh (slab())
     const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error{SBD_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
     return tm;
 }

@@ -1,11 +1,20 @@
 cd $GRAFT_REPO_ROOT
-CMD="python bench.py --steps 3 --warmup 3 --chains-per-gpu 8 --no-cpu-baseline --no-size-sweep --no-extras"
-$CMD > gpurun_out/plain.log 2>&1 || { echo PLAIN FAILED; tail -5 gpurun_out/plain.log; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 70 --csv --log-file gpurun_out/r02_launches.csv $CMD > /dev/null 2>&1; echo launches rc=$?
-ncu --set full --clock-control none -s 100 -c 24 -f -o /tmp/r02_step $CMD > gpurun_out/ncu_full.log 2>&1; echo full rc=$?
-ncu -i /tmp/r02_step.ncu-rep --page raw --csv > gpurun_out/r02_step_raw.csv 2>/dev/null
-ls -la /tmp/r02_step.ncu-rep gpurun_out/r02_step_raw.csv
-for ch in 16 32 64; do
-  C2="python bench.py --steps 2 --warmup 3 --chains-per-gpu $ch --no-cpu-baseline --no-size-sweep --no-extras"
-  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_chamb_multi -s 20 -c 8 --csv --log-file gpurun_out/r02_chamb_traffic_$ch.csv $C2 > /dev/null 2>&1; echo ch $ch rc=$?
-done
+python -m pytest tests -m gpu -x -q -k "cufft or blur or sapg_sizes or golden" > gpurun_out/r02_t7.log 2>&1; tail -4 gpurun_out/r02_t7.log
+CMD="python bench.py --steps 6 --warmup 3 --chains-per-gpu 8 --no-cpu-baseline --no-size-sweep --no-extras"
+$CMD 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value'], d['ms_per_step']); print(d['fused_step']['phase_ms_per_step'])
+"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_cols|k_rows' -s 20 -c 30 --csv --log-file gpurun_out/r02_l7.csv $CMD > /dev/null 2>&1
+python - <<P
+import csv,collections
+rows=[r for r in csv.reader(open('gpurun_out/r02_l7.csv')) if len(r)>10]
+h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value'); 
+d=collections.defaultdict(list)
+for r in rows[1:]:
+    try: d[r[ki][:60]].append(float(r[vi].replace(',','')))
+    except: pass
+for k,v in d.items(): print(k, len(v), round(sum(v)/len(v)/1e3,1),'us', 'max',round(max(v)/1e3,1))
+P
