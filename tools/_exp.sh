@@ -1,20 +1,9 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -x -q -k "cufft or blur or sapg_sizes or golden" > gpurun_out/r02_t7.log 2>&1; tail -4 gpurun_out/r02_t7.log
-CMD="python bench.py --steps 6 --warmup 3 --chains-per-gpu 8 --no-cpu-baseline --no-size-sweep --no-extras"
-$CMD 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print(d['value'], d['ms_per_step']); print(d['fused_step']['phase_ms_per_step'])
-"
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_cols|k_rows' -s 20 -c 30 --csv --log-file gpurun_out/r02_l7.csv $CMD > /dev/null 2>&1
+python -m pytest tests/test_gpu_multigpu.py -m gpu -x -q > gpurun_out/r02_mg.log 2>&1; tail -5 gpurun_out/r02_mg.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29600 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err; tail -3 gpurun_out/r02_bench_n2.err
 python - <<P
-import csv,collections
-rows=[r for r in csv.reader(open('gpurun_out/r02_l7.csv')) if len(r)>10]
-h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value'); 
-d=collections.defaultdict(list)
-for r in rows[1:]:
-    try: d[r[ki][:60]].append(float(r[vi].replace(',','')))
-    except: pass
-for k,v in d.items(): print(k, len(v), round(sum(v)/len(v)/1e3,1),'us', 'max',round(max(v)/1e3,1))
+import json
+for l in open('gpurun_out/r02_bench_n2.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value'], d['ms_per_step'], d['e2e'], d['config']['chains_per_gpu']); print(d.get('config2_laplace_one_image_per_gpu')); print(d['fused_step']['phase_ms_per_step'])
 P
