@@ -71,9 +71,9 @@ def test_salsa_filter_mode_1024(O, cman):
     tau, mu = 0.03 * 4.0, 0.003
     H = cl["H_FFT"](*psi)
     filt = 1.0 / (np.abs(H) ** 2 + mu)
-    from oracle import operators as OP
+    from oracle import operators as OP, salsa
     invLS = lambda z: np.real(OP._ifft2(filt * OP._fft2(z)))
-    want = O.salsa.SALSA_v2(y, lambda z: cl["A"](z, *psi), tau, "MU", mu, "AT", lambda z: cl["AT"](z, *psi),
+    want = salsa.SALSA_v2(y, lambda z: cl["A"](z, *psi), tau, "MU", mu, "AT", lambda z: cl["AT"](z, *psi),
                             "StopCriterion", 1, "True_x", x, "ToleranceA", 1e-5, "MAXITERA", 12, "Phi", O.tv.TVnorm,
                             "TVINITIALIZATION", 1, "TViters", 10, "LS", invLS, "VERBOSE", 0)
     eng = sbd_b200.Engine(n, n, 7, 0, 0.0, max_batch=1)
