@@ -140,6 +140,7 @@ def cpu_oracle_steps(n, steps, warmup, workers, model=0, image=None):
     import oracle
     from oracle import operators as OP
     OP.set_fft(lambda a: scipy.fft.fft2(a, workers=workers), lambda a: scipy.fft.ifft2(a, workers=workers))
+    oracle.tv.set_threads(workers)                  # torchrun exports OMP_NUM_THREADS=1
     x = synthetic_truth(n) if image is None else image
     rng = np.random.default_rng(1)
     stamps = []

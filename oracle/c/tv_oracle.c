@@ -20,6 +20,21 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* number of threads of the loops below (a launcher such as torchrun exports OMP_NUM_THREADS=1);
+ * returns the number now in effect, 1 when built without OpenMP */
+int oc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 static double div_at(const double* px, const double* py, long M, long N, long i, long j) {
     /* :153-154  v = [p2(:,1)  p2(:,2:end-1)-p2(:,1:end-2)  -p2(:,end)]   (p2 = py, along j) */

@@ -38,8 +38,16 @@ def _c():
                                      dp, dp, dp, dp]
         lib.oc_tvnorm.restype = _C.c_double
         lib.oc_tvnorm.argtypes = [dp, _C.c_long, _C.c_long]
+        lib.oc_set_threads.restype = _C.c_int
+        lib.oc_set_threads.argtypes = [_C.c_int]
         _clib = lib
     return _clib
+
+
+def set_threads(n):
+    """Threads of the plain-C loops (torchrun exports OMP_NUM_THREADS=1); returns the number in effect (0: no C lib)."""
+    lib = _c()
+    return int(lib.oc_set_threads(int(n))) if lib else 0
 
 
 def _use_c(npix):
