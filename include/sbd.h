@@ -273,6 +273,9 @@ const char* sbd_phase_name(int i);
  *   "chamb_levels" sweeps fused per launch: 4 (default), 3, 1 = single-sweep kernel
  *   "chamb_emit"   0: separate prox-output pass instead of the tail block writing f
  *   "chamb_plan33" 0: plan K = 4k+1 as 4 x k, 1 instead of 4 x (k-2), 3 x 3
+ *   "chamb_errsub" sampled stop test (the sum of err_k^2 over a subset of the rows already proves err_k > tol;
+ *                  exact fallback otherwise; same k, p and f): 1 whenever the caller does not ask for the value
+ *                  of err (SAPG, sbd_tvprox_dev with err == NULL), 0 never, -1 automatic (large problems only)
  *   "tv_seg"       rows per segment of the TVnorm / single-sweep / output kernels
  *   "geom_chains"  derive the geometry from this many chains instead of the batch
  * sbd_get_geometry: out = {levels, chamb_seg, chamb_grid_x, chamb_grid_y,

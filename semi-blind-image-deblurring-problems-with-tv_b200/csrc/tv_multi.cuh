@@ -20,6 +20,15 @@
 // an err_k within ~1e-15 relative of tol may decide the stop test differently
 // (tests/test_gpu_chambolle_prod.py::test_fused_vs_single_sweep).
 //
+// ERRSUB (sampled stop test): err_k is only ever COMPARED with tol, and err_k^2 is a sum of non-negative terms, so
+// the sum over any SUBSET of the pixels is a lower bound: "subset sum > tol^2" proves err_k > tol and the sweep
+// continues - exactly the reference's decision.  The steady-state loop then forms no err term at all (340 instead of
+// 404 fp64 instructions per trip); the subset is the rows of the generic path at the two ends of every segment.  The
+// dual pair does not depend on err, so p and f are bit-identical.  When the subset does NOT prove it (subset sum <= tol^2: the test is
+// about to fire, or the image is tiny), the block is recomputed with the full sum by the "exact" launch (redo == 2,
+// a no-op otherwise), which decides as before.  Used where the caller does not ask for the value of err (the SAPG
+// loop, sbd_tvprox_dev with err == NULL); the entry points that return err always run the full sum.
+//
 // EMIT: the block that is planned to be the last one also forms the prox output
 // f = g - lambda*div p (chambolle_prox_TV_stop.m:134) from the rows its top level
 // emits, instead of a separate pass over (g, px, py).  div p needs p one pixel to
@@ -84,6 +93,19 @@ __device__ __forceinline__ double seed_with_low_of(double seed, double dead) {
 #ifndef SBD_CM_BIAS
 #define SBD_CM_BIAS 1
 #endif
+// pixels per lane whose err terms the two rows of a trip accumulate under ERRSUB (2 / 1 / 0).  Measured with
+// tools/proto/chamb_bench.cu (ms per 4-level launch, 4096^2 x 8, 128-row segments; full sums: 1.446):
+//   (1,0) 1.56-1.62   (1,1) 1.55   (2,1) 1.41   (2,0) 1.361   (0,2) 1.365   (0,0) 1.35  <- default
+// (one pixel of a lane's pair breaks the stage-by-stage order of the two pixel chains and is SLOWER than the full
+// sums; dropping a whole row's terms gains).  With (0,0) the steady-state loop forms no err term at all and the
+// lower bound is the sum over the rows of the generic path at the segment ends (full terms, ~14 rows per segment):
+// at 4096^2 x 32 chains and 512-row segments 5.65 -> 5.04 ms.
+#ifndef SBD_CM_EMA
+#define SBD_CM_EMA 0
+#endif
+#ifndef SBD_CM_EMB
+#define SBD_CM_EMB 0
+#endif
 #ifndef SBD_CM_REUSE
 #define SBD_CM_REUSE 0
 #endif
@@ -93,7 +115,8 @@ __device__ __forceinline__ double seed_with_low_of(double seed, double dead) {
 #ifndef SBD_CM_OPX0
 #define SBD_CM_OPX0 0
 #endif
-template <class Lv>
+// ERRMODE: which pixels' err terms are formed - 2: both, 1: pixel 0 only, 0: none (ex / ey are then left untouched)
+template <int ERRMODE = 2, class Lv>
 __device__ __forceinline__ void cm_core(const double (&upx)[2], const double (&un)[2], const Lv& h, double tau,
                                         double (&opx)[2], double (&opy)[2], double (&ex)[2], double (&ey)[2]) {
     double upy[2], s2[2], y[2], g[2], rs[2], r[2], t[2], d[2], ee[2];
@@ -129,10 +152,14 @@ __device__ __forceinline__ void cm_core(const double (&upx)[2], const double (&u
 #if !SBD_CM_EARLYD
     CM_V rs[v] = seed_with_low_of(fast_rcp_seed(d[v]), t[v]);                                        // seed from the final d: no early estimate to compute
 #endif
-    CM_V ex[v] = fma(g[v], h.px[v], -upx[v]);                                // :128
-    CM_V ey[v] = fma(g[v], h.py[v], -upy[v]);
+#pragma unroll
+    for (int v = 0; v < ERRMODE; ++v) {
+        ex[v] = fma(g[v], h.px[v], -upx[v]);                                 // :128
+        ey[v] = fma(g[v], h.py[v], -upy[v]);
+    }
     CM_V ee[v] = fma(-d[v], rs[v], 1.0);
 #if SBD_CM_REUSE
+    static_assert(ERRMODE == 2, "SBD_CM_REUSE needs the err terms of both pixels");
     CM_V ee[v] = fma(ee[v], ee[v], ee[v]);
     CM_V rs[v] = fma(rs[v], ee[v], rs[v]);                                   // 1 / (1 + tau |grad u|)
     // :129-130  (p + tau grad u) / d  =  p - (tau / d) (|grad u| p - grad u): the err terms are reused, one fma each
@@ -218,7 +245,7 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
 // the load) and whose u is formed here; the row the level emits goes straight into the new state of
 // the level above (`up`).  A trip of two rows alternates two state sets, so no value is ever copied
 // (the rotating form spent one instruction in six on register moves).  err is not masked here.
-template <bool EDGE>
+template <bool EDGE, int ERRMODE = 2>
 __device__ __forceinline__ void cm_step2(const CmLv& ho, CmLv& hn, CmLv& up, const CmLane& L, double tau, double& err) {
     const double pxl = shfl_up_d(hn.px[1], 1);
     double ux0 = hn.px[0] - pxl, ux1 = hn.px[1] - hn.px[0];                 // :156-157
@@ -236,14 +263,15 @@ __device__ __forceinline__ void cm_step2(const CmLv& ho, CmLv& hn, CmLv& up, con
         if (L.last1) upx[1] = 0.0;
     }
     double ex[2], ey[2];
-    cm_core(upx, hn.u, ho, tau, up.px, up.py, ex, ey);
+    cm_core<ERRMODE>(upx, hn.u, ho, tau, up.px, up.py, ex, ey);
     up.g[0] = ho.g[0]; up.g[1] = ho.g[1];
     if (EDGE) {
         if (!L.in0) { up.px[0] = 0.0; up.py[0] = 0.0; }
         if (!L.in1) { up.px[1] = 0.0; up.py[1] = 0.0; }
     }
     // :128, the four squares go straight into the level's accumulator (one fp64 op per square)
-    err = fma(ex[1], ex[1], fma(ey[1], ey[1], fma(ex[0], ex[0], fma(ey[0], ey[0], err))));
+    if (ERRMODE == 2) err = fma(ex[1], ex[1], fma(ey[1], ey[1], fma(ex[0], ex[0], fma(ey[0], ey[0], err))));
+    else if (ERRMODE == 1) err = fma(ex[0], ex[0], fma(ey[0], ey[0], err));
 }
 
 // ZERO: the incoming dual pair is identically zero (chambolle_prox_TV_stop.m:68-69) and is not loaded
@@ -382,7 +410,7 @@ __device__ __forceinline__ void cm_prefetch(const double* __restrict__ g, const 
 }
 
 // The march of one warp.  nlev <= T levels are applied.
-template <int T, bool EDGE, bool PIPE, bool ZERO, int EMIT>
+template <int T, bool EDGE, bool PIPE, bool ZERO, int EMIT, bool ERRSUB = false>
 __device__ __forceinline__ void cm_march(const double* __restrict__ g, const double* __restrict__ pxi,
                                          const double* __restrict__ pyi, double* __restrict__ pxo,
                                          double* __restrict__ pyo, int nx, int ny, int j0, int j1,
@@ -426,10 +454,11 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
             const double *gl = g + o1, *pxl = pxi + o1, *pyl = pyi + o1;        // next row to load
             double *pxs = pxo + os, *pys = pyo + os, *fs = EMIT ? f + os : nullptr;   // next row to store
             const size_t pfo = (size_t)CM_PF * nx;
-            auto fast_row = [&](int rr, CmLv (&ho)[T], CmLv (&hn)[T]) {
+            auto fast_row = [&](int rr, CmLv (&ho)[T], CmLv (&hn)[T], auto emc) {
+                constexpr int EM = decltype(emc)::value;                        // err terms of this row: 2 / 1 / 0 pixels
                 hn[0].g[0] *= invlam; hn[0].g[1] *= invlam;                     // g / lambda (:124)
                 CmLv top;
-                cm_step2<EDGE>(ho[0], hn[0], T > 1 ? hn[T > 1 ? 1 : 0] : top, L, tau, err[0]);
+                cm_step2<EDGE, EM>(ho[0], hn[0], T > 1 ? hn[T > 1 ? 1 : 0] : top, L, tau, err[0]);
                 // ho[0] is dead from here on: row rr + 1 lands in it
                 if (rr + 1 + CM_PF < ny) cm_prefetch<EDGE, ZERO>(gl, pxl, pyl, pfo, L);
                 {
@@ -441,8 +470,8 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
                 gl += nx; pxl += nx; pyl += nx;
 #pragma unroll
                 for (int s = 1; s < T; ++s) {
-                    if (s + 1 < T) cm_step2<EDGE>(ho[s], hn[s], hn[s + 1 < T ? s + 1 : s], L, tau, err[s]);
-                    else cm_step2<EDGE>(ho[s], hn[s], top, L, tau, err[s]);
+                    if (s + 1 < T) cm_step2<EDGE, EM>(ho[s], hn[s], hn[s + 1 < T ? s + 1 : s], L, tau, err[s]);
+                    else cm_step2<EDGE, EM>(ho[s], hn[s], top, L, tau, err[s]);
                 }
                 CmPk p;
 #pragma unroll
@@ -455,7 +484,12 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
             // (four rows per trip would halve the register moves ptxas leaves at the back edge, but the loop
             // then outgrows the instruction cache close to the SMSP: ncu shows no_instruction stalls and no
             // net gain)
-            for (; r + 1 <= fast_hi; r += 2) { fast_row(r, h, hb); fast_row(r + 1, hb, h); }
+            // ERRSUB: SBD_CM_EMA / SBD_CM_EMB pixels of the two rows (any subset is a valid lower bound of err_k^2)
+            constexpr int EMA = ERRSUB ? SBD_CM_EMA : 2, EMB = ERRSUB ? SBD_CM_EMB : 2;
+            for (; r + 1 <= fast_hi; r += 2) {
+                fast_row(r, h, hb, std::integral_constant<int, EMA>{});
+                fast_row(r + 1, hb, h, std::integral_constant<int, EMB>{});
+            }
 #pragma unroll
             for (int v = 0; v < 2; ++v) { nxt.px[v] = hb[0].px[v]; nxt.py[v] = hb[0].py[v]; nxt.g[v] = hb[0].g[v]; }   // raw row r
             // the fast rows add their err terms unmasked: lanes outside the output region hold 0
@@ -471,8 +505,10 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
 
 // grid = (ceil(nstrips / TV_WARPS), nsegs, batch); block = TV_THREADS.
 // redo == 0: main launch of a block of T sweeps; redo == 1: re-run with the
-// number of levels the stop test asked for (no-op unless st.redo != 0).
-template <int T, bool PIPE, int MINB, bool ZERO, int EMIT>
+// number of levels the stop test asked for (no-op unless st.redo > 0);
+// redo == 2: "exact" launch behind an ERRSUB main launch - recomputes the block with the full err sums and decides
+// (no-op unless the sampled sums left the decision open, st.redo == -1).
+template <int T, bool PIPE, int MINB, bool ZERO, int EMIT, bool ERRSUB = false>
 __global__ void __launch_bounds__(TV_THREADS, MINB)
 k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, const double* __restrict__ pyi,
               double* __restrict__ pxo, double* __restrict__ pyo, int nx, int ny, int seg, int nstrips,
@@ -485,9 +521,12 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
     const int img = blockIdx.z;
     ChambState* S = st + img;
     int nlev;
-    if (redo) {
+    if (redo == 1) {
         nlev = S->redo;
-        if (nlev == 0) return;
+        if (nlev <= 0) return;
+    } else if (redo == 2) {
+        if (S->redo != -1) return;
+        nlev = min(T, ctl->maxiter - S->k);
     } else {
         if (S->done) return;
         nlev = min(T, ctl->maxiter - S->k);
@@ -513,8 +552,8 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
         L.central = cen && (L.in0 || L.in1);
         const int j0 = blockIdx.y * seg, j1 = min(j0 + seg, ny);
         const bool edge = (i0 < 0) || (i0 + 64 > nx);
-        if (edge) cm_march<T, true, PIPE, ZERO, EMIT>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err, f, lambda);
-        else      cm_march<T, false, PIPE, ZERO, EMIT>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err, f, lambda);
+        if (edge) cm_march<T, true, PIPE, ZERO, EMIT, ERRSUB>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err, f, lambda);
+        else      cm_march<T, false, PIPE, ZERO, EMIT, ERRSUB>(g, pxi, pyi, pxo, pyo, nx, ny, j0, j1, L, invlam, tau, nlev, err, f, lambda);
     }
 
     block_sum<T>(err, sm);
@@ -531,23 +570,28 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
             for (int s = 0; s < T; ++s) e[s] = sqrt(warp_sum_partials(part + (size_t)s * nparts, (int)nparts, 1));   // :128
             if (threadIdx.x == 0) {
                 const int k0 = S->k;
-                if (redo) {                         // the stop sweep was decided by the main launch
+                if (redo == 1) {                    // the stop sweep was decided by the main launch
                     S->k = k0 + nlev; S->done = 1; S->redo = 0; S->buf ^= 1;
                 } else {
                     int stop = 0;
+                    bool open = false;              // ERRSUB: a sampled sum <= tol^2 proves nothing
                     double estop = 0.0, elast = 0.0;
 #pragma unroll
                     for (int s = 1; s <= T; ++s) {
-                        if (s <= nlev) {
-                            const bool cont = (k0 + s < ctl->maxiter) && (e[s - 1] > ctl->tol);   // :131
-                            if (!cont && stop == 0) { stop = s; estop = e[s - 1]; }
+                        if (s <= nlev && stop == 0 && !open) {
+                            const bool more = k0 + s < ctl->maxiter;
+                            const bool cont = more && (e[s - 1] > ctl->tol);                      // :131
+                            if (ERRSUB && more && !cont) open = true;                             // decided by the exact launch
+                            else if (!cont) { stop = s; estop = e[s - 1]; }
                             elast = e[s - 1];
                         }
                     }
-                    if (stop == 0) {                // all nlev sweeps continue
-                        S->k = k0 + nlev; S->err = elast; S->buf ^= 1;
+                    if (ERRSUB && open) {
+                        S->redo = -1;               // nothing advances: the exact launch recomputes this block
+                    } else if (stop == 0) {         // all nlev sweeps continue
+                        S->k = k0 + nlev; S->err = elast; S->buf ^= 1; S->redo = 0;
                     } else if (stop == nlev) {      // stops exactly at the end of this block
-                        S->k = k0 + nlev; S->err = estop; S->done = 1; S->buf ^= 1;
+                        S->k = k0 + nlev; S->err = estop; S->done = 1; S->buf ^= 1; S->redo = 0;
                         if (EMIT) S->emitted = 1;   // f written above is the prox output
                     } else {                        // stopped inside the block: redo with `stop` levels
                         S->err = estop; S->redo = stop;

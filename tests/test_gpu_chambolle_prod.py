@@ -223,3 +223,78 @@ def test_geometry_independent_of_sharding(sbd):
     eng.set_option("geom_chains", 0)
     assert eng.geometry(2)["chamb_seg"] != want["chamb_seg"] or eng.geometry(2)["tv_seg"] != want["tv_seg"]
     eng.close()
+
+
+# ------------------------------------------------------------------ sampled stop test (ERRSUB)
+def _dev_prox(eng, g, lam, K, tol, want_err):
+    """sbd_tvprox_dev on a batch; err == NULL lets the engine use the sampled stop test."""
+    import torch
+    from sbd_b200._lib import lib
+    B = g.shape[0]
+    gd = torch.from_numpy(np.ascontiguousarray(g.transpose(0, 2, 1))).cuda()
+    fd = torch.empty_like(gd)
+    it = (C.c_int * B)(); er = (C.c_double * B)()
+    rc = lib.sbd_tvprox_dev(eng._h, gd.data_ptr(), lam, K, tol, 0.249, fd.data_ptr(), it, er if want_err else None, B)
+    assert rc == 0, lib.sbd_last_error(eng._h)
+    lib.sbd_synchronize(eng._h)
+    return fd.cpu().numpy().transpose(0, 2, 1), list(it)
+
+
+@pytest.mark.parametrize("shape,seg", [((128, 256), 32), ((130, 300), 128)])
+def test_sampled_stop_test_is_exact(sbd, O, shape, seg):
+    """ERRSUB: err_k^2 summed over a subset of the rows is a lower bound, so 'sampled sum > tol^2' is the reference's
+    own decision; when it proves nothing the block is recomputed exactly.  For every stop position 1..25 (and no stop)
+    the sweep count must be the oracle's and f bit-identical to the run with the full sums."""
+    g = natural(shape, 21)
+    gb = np.stack([g, natural(shape, 22)])
+    eng = sbd.Engine(shape[0], shape[1], 1, 0, 0.0, max_batch=2)
+    eng.set_option("chamb_seg", seg)
+    errs = []
+    for kstop in range(1, 26):
+        _, _, _, _, e_k = O.tv.chambolle_prox_TV_stop(g, "lambda", 0.3, "maxiter", kstop, "tol", 0.0, return_info=True)
+        errs.append(e_k)
+    tols = [errs[k - 1] * (1 + 1e-9) for k in range(1, 26) if k == 1 or errs[k - 1] < min(errs[:k - 1])] + [1e-3, errs[-1] * 0.5]
+    for K in (25, 22):
+        for tol in tols:
+            eng.set_option("chamb_errsub", 0)
+            f_full, k_full = _dev_prox(eng, gb, 0.3, K, tol, want_err=False)
+            eng.set_option("chamb_errsub", 1)
+            f_sub, k_sub = _dev_prox(eng, gb, 0.3, K, tol, want_err=False)
+            assert k_sub == k_full, (K, tol, k_sub, k_full)
+            assert np.array_equal(f_sub, f_full)
+            for b in range(2):
+                fo, _, _, ko, _ = O.tv.chambolle_prox_TV_stop(gb[b], "lambda", 0.3, "maxiter", K, "tol", tol, return_info=True)
+                assert k_sub[b] == ko and rel(f_sub[b], fo) < TOL_F
+    # the entry that returns err always runs the full sums, whatever the option says
+    f, px, py, k, err = eng.tvprox(g, 0.3, 25)
+    _, _, _, ko, eo = O.tv.chambolle_prox_TV_stop(g, "lambda", 0.3, "maxiter", 25, return_info=True)
+    assert k == ko and abs(err - eo) <= TOL_E * eo
+    eng.close()
+
+
+def test_sampled_stop_test_in_sapg_laplace(sbd, O, boat):
+    """SAPG Laplace (lambda*theta starts at 1e-3: the stop test fires in the prox) with the sampled test forced on:
+    same sweep counts and trajectories as the oracle."""
+    x = boat[128:384, 128:384]
+    rng = np.random.default_rng(31)
+    tape = []
+
+    def randn(shape):
+        z = rng.standard_normal(shape); tape.append(z); return z
+
+    y, op = O.operators.setup_demo(2, x, randn, samples=10, warmup=4, burnIn=6)
+    del tape[:]
+    th, b, s2, r = O.sapg.SAPG_algorithm_laplace(y, op, randn)
+    noise = np.stack(tape)[:, None]
+    eng = sbd.Engine(256, 256, 7, 2, 0.0, max_batch=1)
+    eng.set_option("chamb_errsub", 1)
+    eng.set_option("chamb_seg", 32)
+    _, _, _, g = sbd.SAPG_algorithm_laplace(y, op, noise=noise, engine=eng)
+    for k in ("thetas", "bs", "sigmas", "logPiTraceX", "gXTrace"):
+        assert rel(g[k], r[k]) < 1e-6, k
+    assert rel(g["X_sample"], r["X_sample"]) < 1e-6
+    assert g["chambolle_iters"].min() < 25
+    eng.set_option("chamb_errsub", 0)
+    _, _, _, g0 = sbd.SAPG_algorithm_laplace(y, op, noise=noise, engine=eng)
+    assert np.array_equal(g0["chambolle_iters"], g["chambolle_iters"]) and np.array_equal(g0["thetas"], g["thetas"])
+    eng.close()

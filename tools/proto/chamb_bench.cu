@@ -2,6 +2,9 @@
 // (4096^2, `batch` chains, 128-row segments), for A/B-ing variants of tv_multi.cuh built with -D switches.
 // build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr -I../../semi-blind-image-deblurring-problems-with-tv_b200/csrc -o chamb_bench chamb_bench.cu
 #include "tv_multi.cuh"
+#ifndef HARNESS_ERRSUB
+#define HARNESS_ERRSUB false
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -33,7 +36,7 @@ int main(int argc, char** argv) {
     auto run = [&](int i) {
         const double* pxi = (i & 1) ? px1 : px0; const double* pyi = (i & 1) ? py1 : py0;
         double* pxo = (i & 1) ? px0 : px1; double* pyo = (i & 1) ? py0 : py1;
-        k_chamb_multi<4, false, 3, false, 0><<<grid, TV_THREADS>>>(g, pxi, pyi, pxo, pyo, n, n, seg, strips, npix, ctl, st, part, 0, nullptr);
+        k_chamb_multi<4, false, 3, false, 0, HARNESS_ERRSUB><<<grid, TV_THREADS>>>(g, pxi, pyi, pxo, pyo, n, n, seg, strips, npix, ctl, st, part, 0, nullptr);
     };
     for (int i = 0; i < 4; ++i) run(i);
     CK(cudaDeviceSynchronize());
