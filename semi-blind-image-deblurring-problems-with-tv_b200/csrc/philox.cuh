@@ -28,7 +28,7 @@ __device__ __forceinline__ double2 philox_normal2(uint64_t seed, uint32_t stream
     const double u2 = ((double)b + 0.5) * 0x1p-53;
     const double r = sqrt(-2.0 * log(u1));
     double s, c;
-    sincos(6.283185307179586476925286766559 * u2, &s, &c);
+    sincospi(2.0 * u2, &s, &c);         // = sincos(2 pi u2) to rounding, without the argument reduction of a general angle
     return make_double2(r * c, r * s);
 }
 

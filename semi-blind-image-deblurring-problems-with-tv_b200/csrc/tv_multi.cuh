@@ -100,6 +100,9 @@ __device__ __forceinline__ double seed_with_low_of(double seed, double dead) {
 // sums; dropping a whole row's terms gains).  With (0,0) the steady-state loop forms no err term at all and the
 // lower bound is the sum over the rows of the generic path at the segment ends (full terms, ~14 rows per segment):
 // at 4096^2 x 32 chains and 512-row segments 5.65 -> 5.04 ms.
+#ifndef SBD_CM_KREG
+#define SBD_CM_KREG 1
+#endif
 #ifndef SBD_CM_EMA
 #define SBD_CM_EMA 0
 #endif
@@ -115,10 +118,25 @@ __device__ __forceinline__ double seed_with_low_of(double seed, double dead) {
 #ifndef SBD_CM_OPX0
 #define SBD_CM_OPX0 0
 #endif
+// The two fp64 constants of the level step that have no short immediate form.  ptxas rebuilds a literal with two MOVs at
+// every use inside the loop (16 MOVs per trip); read once through an opaque asm they stay in registers (SBD_CM_KREG).
+struct CmK { double c375, tiny; };
+__device__ __forceinline__ CmK cm_consts() {
+    CmK k;
+#if SBD_CM_KREG
+    asm volatile("mov.f64 %0, 0d3FD8000000000000;" : "=d"(k.c375));
+    asm volatile("mov.f64 %0, 0d01A56E1FC2F8F359;" : "=d"(k.tiny));
+#else
+    k.c375 = 0.375; k.tiny = 1e-300;
+#endif
+    return k;
+}
+__device__ __forceinline__ CmK cm_consts_plain() { CmK k; k.c375 = 0.375; k.tiny = 1e-300; return k; }
 // ERRMODE: which pixels' err terms are formed - 2: both, 1: pixel 0 only, 0: none (ex / ey are then left untouched)
 template <int ERRMODE = 2, class Lv>
 __device__ __forceinline__ void cm_core(const double (&upx)[2], const double (&un)[2], const Lv& h, double tau,
-                                        double (&opx)[2], double (&opy)[2], double (&ex)[2], double (&ey)[2]) {
+                                        double (&opx)[2], double (&opy)[2], double (&ex)[2], double (&ey)[2],
+                                        const CmK& K) {
     double upy[2], s2[2], y[2], g[2], rs[2], r[2], t[2], d[2], ee[2];
     const double mtau = -tau;
 #define CM_V _Pragma("unroll") for (int v = 0; v < 2; ++v)
@@ -128,7 +146,7 @@ __device__ __forceinline__ void cm_core(const double (&upx)[2], const double (&u
     // exactly 0, which changes nothing that is representable: d = 1, p unchanged, err += 1e-300 |p|^2); for any
     // other value the bias is below half an ulp.  It replaces an integer clamp of the seed's high word.
 #if SBD_CM_BIAS
-    CM_V sq[v] = fma(upy[v], upy[v], 1e-300);
+    CM_V sq[v] = fma(upy[v], upy[v], K.tiny);
     CM_V s2[v] = fma(upx[v], upx[v], sq[v]);
     CM_V y[v] = seed_with_low_of(fast_rsqrt_seed(s2[v]), sq[v]);
 #else
@@ -145,7 +163,7 @@ __device__ __forceinline__ void cm_core(const double (&upx)[2], const double (&u
     CM_V rs[v] = seed_with_low_of(fast_rcp_seed(d0[v]), sq[v]);
 #endif
     CM_V r[v] = fma(-g[v], y[v], 1.0);
-    CM_V t[v] = fma(r[v], 0.375, 0.5);
+    CM_V t[v] = fma(r[v], K.c375, 0.5);
     CM_V t[v] = r[v] * t[v];                                                 // r + 1.5 r^2
     CM_V g[v] = fma(g[v], t[v], g[v]);                                       // :127
     CM_V d[v] = fma(tau, g[v], 1.0);
@@ -225,7 +243,7 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
     }
     CmPk o;
     double ex[2], ey[2];
-    cm_core(upx, un, h, tau, o.px, o.py, ex, ey);
+    cm_core(upx, un, h, tau, o.px, o.py, ex, ey, cm_consts_plain());
 #pragma unroll
     for (int v = 0; v < 2; ++v) o.g[v] = h.g[v];
     const double e = fma(ex[1], ex[1], fma(ey[1], ey[1], fma(ex[0], ex[0], ey[0] * ey[0])));      // :128
@@ -246,7 +264,8 @@ __device__ __forceinline__ void cm_step(CmLv& h, CmPk& p, const CmLane& L, doubl
 // the level above (`up`).  A trip of two rows alternates two state sets, so no value is ever copied
 // (the rotating form spent one instruction in six on register moves).  err is not masked here.
 template <bool EDGE, int ERRMODE = 2>
-__device__ __forceinline__ void cm_step2(const CmLv& ho, CmLv& hn, CmLv& up, const CmLane& L, double tau, double& err) {
+__device__ __forceinline__ void cm_step2(const CmLv& ho, CmLv& hn, CmLv& up, const CmLane& L, double tau, double& err,
+                                         const CmK& K) {
     const double pxl = shfl_up_d(hn.px[1], 1);
     double ux0 = hn.px[0] - pxl, ux1 = hn.px[1] - hn.px[0];                 // :156-157
     if (EDGE) {
@@ -263,7 +282,7 @@ __device__ __forceinline__ void cm_step2(const CmLv& ho, CmLv& hn, CmLv& up, con
         if (L.last1) upx[1] = 0.0;
     }
     double ex[2], ey[2];
-    cm_core<ERRMODE>(upx, hn.u, ho, tau, up.px, up.py, ex, ey);
+    cm_core<ERRMODE>(upx, hn.u, ho, tau, up.px, up.py, ex, ey, K);
     up.g[0] = ho.g[0]; up.g[1] = ho.g[1];
     if (EDGE) {
         if (!L.in0) { up.px[0] = 0.0; up.py[0] = 0.0; }
@@ -454,11 +473,12 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
             const double *gl = g + o1, *pxl = pxi + o1, *pyl = pyi + o1;        // next row to load
             double *pxs = pxo + os, *pys = pyo + os, *fs = EMIT ? f + os : nullptr;   // next row to store
             const size_t pfo = (size_t)CM_PF * nx;
+            const CmK KK = cm_consts();
             auto fast_row = [&](int rr, CmLv (&ho)[T], CmLv (&hn)[T], auto emc) {
                 constexpr int EM = decltype(emc)::value;                        // err terms of this row: 2 / 1 / 0 pixels
                 hn[0].g[0] *= invlam; hn[0].g[1] *= invlam;                     // g / lambda (:124)
                 CmLv top;
-                cm_step2<EDGE, EM>(ho[0], hn[0], T > 1 ? hn[T > 1 ? 1 : 0] : top, L, tau, err[0]);
+                cm_step2<EDGE, EM>(ho[0], hn[0], T > 1 ? hn[T > 1 ? 1 : 0] : top, L, tau, err[0], KK);
                 // ho[0] is dead from here on: row rr + 1 lands in it
                 if (rr + 1 + CM_PF < ny) cm_prefetch<EDGE, ZERO>(gl, pxl, pyl, pfo, L);
                 {
@@ -470,8 +490,8 @@ __device__ __forceinline__ void cm_march(const double* __restrict__ g, const dou
                 gl += nx; pxl += nx; pyl += nx;
 #pragma unroll
                 for (int s = 1; s < T; ++s) {
-                    if (s + 1 < T) cm_step2<EDGE, EM>(ho[s], hn[s], hn[s + 1 < T ? s + 1 : s], L, tau, err[s]);
-                    else cm_step2<EDGE, EM>(ho[s], hn[s], top, L, tau, err[s]);
+                    if (s + 1 < T) cm_step2<EDGE, EM>(ho[s], hn[s], hn[s + 1 < T ? s + 1 : s], L, tau, err[s], KK);
+                    else cm_step2<EDGE, EM>(ho[s], hn[s], top, L, tau, err[s], KK);
                 }
                 CmPk p;
 #pragma unroll
