@@ -1,11 +1,11 @@
 cd $GRAFT_REPO_ROOT
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; tail -2 gpurun_out/r02_bench_n1.err
-CMD="python bench.py --steps 3 --warmup 3 --chains-per-gpu 8 --no-cpu-baseline --no-size-sweep --no-extras"
-$CMD > gpurun_out/plain.log 2>&1 || { echo PLAIN FAILED; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 90 --csv --log-file gpurun_out/r02_launches.csv $CMD > /dev/null 2>&1; echo launches rc=$?
-ncu --set full --clock-control none -s 140 -c 32 -f -o /tmp/r02_step $CMD > gpurun_out/ncu_full.log 2>&1; echo full rc=$?
-ncu -i /tmp/r02_step.ncu-rep --page raw --csv > gpurun_out/r02_step_raw.csv 2>/dev/null
-for ch in 16 32 64; do
-  C2="python bench.py --steps 2 --warmup 3 --chains-per-gpu $ch --no-cpu-baseline --no-size-sweep --no-extras"
-  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:k_chamb_multi -s 30 -c 9 --csv --log-file gpurun_out/r02_chamb_traffic_$ch.csv $C2 > /dev/null 2>&1; echo ch $ch rc=$?
-done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29610 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; tail -2 gpurun_out/r02_bench_n8.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r02_bench_n4.json 2> gpurun_out/r02_bench_n4.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err
+python - <<P
+import json
+for n in (2,4,8):
+    for l in open(f'gpurun_out/r02_bench_n{n}.json'):
+        if l.startswith('{'):
+            d=json.loads(l); print(n, round(d['value'],1), round(d['ms_per_step'],2), round(d['e2e']['value'],1), d['config']['chains_per_gpu'], d['clocks']['sm_mhz'], d.get('config2_laplace_one_image_per_gpu',{}).get('image_steps_per_s_device'))
+P
