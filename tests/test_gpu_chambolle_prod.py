@@ -298,3 +298,14 @@ def test_sampled_stop_test_in_sapg_laplace(sbd, O, boat):
     _, _, _, g0 = sbd.SAPG_algorithm_laplace(y, op, noise=noise, engine=eng)
     assert np.array_equal(g0["chambolle_iters"], g["chambolle_iters"]) and np.array_equal(g0["thetas"], g["thetas"])
     eng.close()
+
+
+def test_set_option_rejects_unknown_names(sbd):
+    from sbd_b200 import SbdError
+    eng = sbd.Engine(64, 64, 1, 0, 0.0, max_batch=1)
+    with pytest.raises(SbdError):
+        eng.set_option("no_such_option", 1)
+    for name in ("chamb_seg", "chamb_levels", "chamb_emit", "chamb_plan33", "chamb_errsub", "tv_seg", "geom_chains"):
+        eng.set_option(name, -1 if name != "geom_chains" else 0)
+    assert eng.geometry(1)["levels"] == 4
+    eng.close()

@@ -1,11 +1,19 @@
 cd $GRAFT_REPO_ROOT
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29610 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; tail -2 gpurun_out/r02_bench_n8.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r02_bench_n4.json 2> gpurun_out/r02_bench_n4.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err
-python - <<P
-import json
-for n in (2,4,8):
-    for l in open(f'gpurun_out/r02_bench_n{n}.json'):
-        if l.startswith('{'):
-            d=json.loads(l); print(n, round(d['value'],1), round(d['ms_per_step'],2), round(d['e2e']['value'],1), d['config']['chains_per_gpu'], d['clocks']['sm_mhz'], d.get('config2_laplace_one_image_per_gpu',{}).get('image_steps_per_s_device'))
-P
+L=semi-blind-image-deblurring-problems-with-tv_b200/lib/libsbd.so
+cp $L /tmp/cur.so
+run() {
+python bench.py --steps 8 --warmup 3 --chains-per-gpu $1 --no-cpu-baseline --no-size-sweep --no-extras 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(round(d['value'],1), round(d['ms_per_step'],3), d['clocks']['sm_mhz'], {k:round(v,2) for k,v in d['fused_step']['phase_ms_per_step'].items()})
+"
+}
+for rep in 1 2; do
+for v in cur split; do
+  if [ $v = cur ]; then cp /tmp/cur.so $L; else cp tools/proto/libsbd_split.so $L; fi
+  echo "== $v"; run 8; run 64
+done; done
+cp tools/proto/libsbd_split.so $L
+python -m pytest tests -m gpu -x -q > gpurun_out/r02_t10.log 2>&1; tail -5 gpurun_out/r02_t10.log
+cp /tmp/cur.so $L
