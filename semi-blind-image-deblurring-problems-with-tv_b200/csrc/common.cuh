@@ -41,6 +41,11 @@ struct Control {
     unsigned int draw;          // Philox step counter (number of noise images drawn so far per chain)
     int post_n;                 // samples accumulated in the posterior mean
     int phase;                  // 0 warm-up, 1 main
+    // The prox of an iteration runs on its own stream next to the analysis of the new sample and the scalar update
+    // (sbd.cu): it works from a SNAPSHOT of lambda*theta taken by k_chamb_reset, and counts its own calls
+    double prox_lambda_run;     // lambda*theta of the prox in flight
+    int prox_count;             // slot of the chamb_k trace the next main-loop prox fills
+    int pad_;
 };
 
 struct ChambState {             // one per image / chain

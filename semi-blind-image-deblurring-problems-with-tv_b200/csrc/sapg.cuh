@@ -107,6 +107,7 @@ __global__ void k_sapg_scalar(int mode, const SapgConst c, Control* __restrict__
             tr.thetas[0] = th; tr.sigmas[0] = s2; tr.psi0[0] = ctl->psi[0]; tr.psi1[0] = ctl->psi[1];
             tr.sqerr[0] = sq;
             tr.chamb_k[0] = chst[0].k;
+            ctl->prox_count = 1;                                        // slot of the first main-loop prox (k_chamb_record)
             ctl->ii = 2;
             ctl->phase = 1;
             ctl->post_n = 0;
@@ -132,8 +133,7 @@ __global__ void k_sapg_scalar(int mode, const SapgConst c, Control* __restrict__
             tr.g_theta[k] = G_t; tr.g_psi0[k] = G_0; tr.g_psi1[k] = G_1; tr.g_sigma[k] = G_s;  // :197-200
             tr.logPi[k] = logpi;                                                            // :207
             tr.gX[k - 1] = gx;                                                              // :208 (Q22)
-            tr.sqerr[k] = sq;
-            tr.chamb_k[k] = chst[0].k;
+            tr.sqerr[k] = sq;                                                               // (chamb_k[k]: k_chamb_record)
             ctl->theta = thn; ctl->sigma2 = s2n; ctl->psi[0] = psn[0]; ctl->psi[1] = psn[1];
             ctl->prox_lambda_theta = c.prox_lambda * thn;
             ctl->inv_scale = 1.0 / (s2n * c.dimX);

@@ -126,6 +126,10 @@ struct sbd_ctx {
     double *sal_aty = nullptr, *sal_u = nullptr, *sal_bu = nullptr, *sal_xt = nullptr;   // SALSA images
     cudaStream_t copy_stream = nullptr;                     // device -> host copy of the last samples, overlapped
     cudaEvent_t ev_langevin = nullptr;
+    cudaStream_t prox_stream = nullptr;                     // the prox of an iteration runs here, next to the analysis
+    cudaEvent_t ev_fork = nullptr, ev_reset = nullptr, ev_join = nullptr;
+    int opt_overlap = -1;                                   // -1 automatic (on unless profiling), 0 off
+    bool arm_ev_reset = false;
 
     // comm
     nccl_comm comm = nullptr;
@@ -295,6 +299,13 @@ void ensure_ws(sbd_ctx* c, int batch) {
     c->ws_batch = batch;
 }
 
+// launches issued inside the scope go to another stream of the context
+struct StreamScope {
+    sbd_ctx* c; cudaStream_t old;
+    StreamScope(sbd_ctx* c_, cudaStream_t s) : c(c_), old(c_->stream) { c->stream = s; }
+    ~StreamScope() { c->stream = old; }
+};
+
 // Phase timing without perturbing the run: event pairs are only RECORDED while
 // the iteration is being enqueued and resolved after the run has finished.
 struct PhaseTimer {
@@ -365,8 +376,9 @@ void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const do
 void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, bool zero_start, bool keep_duals = true,
                bool want_err = true) {
     SBD_REQUIRE(maxiter >= 1, SBD_E_INVALID, "chambolle: maxiter must be >= 1");       // the block plan below relies on it
-    k_chamb_reset<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->chst, batch);
+    k_chamb_reset<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->chst, batch, c->ctl);
     LAUNCH_CHECK(c);
+    if (c->arm_ev_reset) SBD_CUDA(cudaEventRecord(c->ev_reset, c->stream));     // the lambda*theta snapshot is taken
     dim3 grid(c->tv_gx, c->tv_gy, batch);
     PhaseTimer* pt = new PhaseTimer(c, 2);
     if (c->cmT > 1) {
@@ -646,6 +658,7 @@ int sbd_set_option(sbd_ctx* c, const char* name, int value) {
     else if (n == "chamb_emit") c->opt_chamb_emit = value;
     else if (n == "chamb_plan33") c->opt_chamb_plan33 = value;
     else if (n == "chamb_errsub") c->opt_chamb_errsub = value;
+    else if (n == "overlap") c->opt_overlap = value;
     else if (n == "geom_chains") c->geom_total = std::max(value, 0);
     else { c->err = "sbd_set_option: unknown option '" + n + "'"; return SBD_E_INVALID; }
     c->geom_batch = -1;             // recomputed by the next call
@@ -729,6 +742,11 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
         SBD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         SBD_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         SBD_CUDA(cudaEventCreateWithFlags(&c->ev_langevin, cudaEventDisableTiming));
+        SBD_CUDA(cudaStreamCreateWithFlags(&c->prox_stream, cudaStreamNonBlocking));
+        SBD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        SBD_CUDA(cudaEventCreateWithFlags(&c->ev_reset, cudaEventDisableTiming));
+        SBD_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        if (const char* e = getenv("SBD_OVERLAP")) c->opt_overlap = atoi(e);
         {
             int dev = 0;
             SBD_CUDA(cudaGetDevice(&dev));
@@ -770,6 +788,10 @@ int sbd_destroy(sbd_ctx* c) {
     dfree(c->trace_d); dfree(c->trace_i); dfree(c->sal_aty); dfree(c->sal_u); dfree(c->sal_bu); dfree(c->sal_xt);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_langevin) cudaEventDestroy(c->ev_langevin);
+    if (c->prox_stream) { cudaStreamSynchronize(c->prox_stream); cudaStreamDestroy(c->prox_stream); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_reset) cudaEventDestroy(c->ev_reset);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return SBD_OK;
@@ -1335,23 +1357,11 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
         PhaseTimer pt(c, 3);
         chambolle(c, c->X, c->P, nch, prm->chambolle_maxiter, true, false, false);    // zero start: chambolle_prox_TV_stop.m:68-69
     };
-    auto myula_step = [&]() {
-        { PhaseTimer pt(c, 0);
-          cols<COL_MUL_INV>(c, c->S1, c->S2, nch);                 // gradF with the current parameters
-          rows_inv(c, c->S2, c->Gf, nch); }
-        { PhaseTimer pt(c, 1);
-          const unsigned gx = (unsigned)((c->npix / 2 + 255) / 256);
-          k_langevin<<<dim3(gx, nch), 256, 0, s>>>(c->X, c->P, c->Gf, d_noise, post, c->ctl, k.gam, k.lamb, k.sq2gam,
-                                                   c->npix, nch, prm->seed, prm->chain_offset, burnIn);
-          LAUNCH_CHECK(c);
-          if (mark_langevin) SBD_CUDA(cudaEventRecord(c->ev_langevin, s)); }
-        prox();
-        analyse(c, nch);
-        if (d_xtrue) {
-            k_sqdiff<<<dim3(256, nch), 256, 0, s>>>(c->X, d_xtrue, c->npix, c->part_sq, c->cnt_sq, c->stats);
-            LAUNCH_CHECK(c);
-        }
-        gather_stats(c, nch, &gstats);
+    // gradF with the CURRENT parameters from the spectrum of the current sample (S1): what the next Langevin update uses
+    auto gradient = [&]() {
+        PhaseTimer pt(c, 0);
+        cols<COL_MUL_INV>(c, c->S1, c->S2, nch);
+        rows_inv(c, c->S2, c->Gf, nch);
     };
     auto scalar = [&](int mode) {
         PhaseTimer pt(c, 6);
@@ -1359,28 +1369,74 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
         LAUNCH_CHECK(c);
         if (mode == 2) psf_refresh_coef(c, c->nk);
     };
+    // One MYULA iteration, starting at its Langevin update (the gradient it needs was formed by the previous unit):
+    //     X <- Langevin(X, prox, gradF)                                     Guassian.m:160-161
+    //     prox(X, theta_old)                                                :162        } independent of each other:
+    //     statistics of X, [all-gather,] scalar update, gradF(new params)   :165-208    } two streams
+    // The prox only READS X and its own buffers and works from a snapshot of lambda*theta (k_chamb_reset), so it runs
+    // on prox_stream next to the analysis of the same sample, the parameter update and the next gradient - the
+    // memory-bound FFT passes fill the issue-bound Chambolle sweeps.  Same kernels, same order per buffer: results
+    // are bit-identical to the serial order (SBD_OVERLAP=0 / sbd_set_option("overlap", 0); profiling runs serially).
+    auto unit = [&](int mode, bool grad_after) {
+        { PhaseTimer pt(c, 1);
+          const unsigned gx = (unsigned)((c->npix / 2 + 255) / 256);
+          k_langevin<<<dim3(gx, nch), 256, 0, s>>>(c->X, c->P, c->Gf, d_noise, post, c->ctl, k.gam, k.lamb, k.sq2gam,
+                                                   c->npix, nch, prm->seed, prm->chain_offset, burnIn);
+          LAUNCH_CHECK(c);
+          if (mark_langevin) SBD_CUDA(cudaEventRecord(c->ev_langevin, s)); }
+        const bool ov = c->opt_overlap != 0 && !c->profile;
+        if (ov) {
+            SBD_CUDA(cudaEventRecord(c->ev_fork, s));
+            SBD_CUDA(cudaStreamWaitEvent(c->prox_stream, c->ev_fork, 0));
+            {
+                StreamScope sc(c, c->prox_stream);
+                c->arm_ev_reset = true;
+                try { prox(); } catch (...) { c->arm_ev_reset = false; throw; }
+                c->arm_ev_reset = false;
+                if (mode == 2) { k_chamb_record<<<1, 1, 0, c->stream>>>(c->chst, c->ctl, dt.t.chamb_k, samples); LAUNCH_CHECK(c); }
+                SBD_CUDA(cudaEventRecord(c->ev_join, c->stream));
+            }
+        } else {
+            prox();
+            if (mode == 2) { k_chamb_record<<<1, 1, 0, s>>>(c->chst, c->ctl, dt.t.chamb_k, samples); LAUNCH_CHECK(c); }
+        }
+        analyse(c, nch);
+        if (d_xtrue) {
+            k_sqdiff<<<dim3(256, nch), 256, 0, s>>>(c->X, d_xtrue, c->npix, c->part_sq, c->cnt_sq, c->stats);
+            LAUNCH_CHECK(c);
+        }
+        gather_stats(c, nch, &gstats);
+        if (ov) SBD_CUDA(cudaStreamWaitEvent(s, c->ev_reset, 0));    // the prox has its snapshot of lambda*theta
+        scalar(mode);
+        if (grad_after) gradient();
+        if (ov) SBD_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    };
 
-    // n iterations of (MYULA step + scalar kernel `mode`).  With use_graph the fixed launch sequence of
-    // one iteration (all scalars are device-resident) is captured once and replayed: at small image
-    // sizes the iteration is launch-bound and the graph removes most of the per-launch CPU cost.
-    // `mark_last`: record ev_langevin right after the Langevin kernel of the LAST iteration (that iteration is
-    // then launched eagerly), so that the copy of the last samples can overlap its prox / spectral analysis.
-    auto run_loop = [&](int n, int mode, bool mark_last) {
+    // n iterations.  With use_graph the fixed launch sequence of one iteration (all scalars are device-resident, both
+    // streams) is captured once and replayed: at small image sizes the iteration is launch-bound and the graph
+    // removes most of the per-launch CPU cost.
+    // `last_of_run`: the last iteration is launched eagerly, records ev_langevin right after its Langevin kernel (so
+    // that the copy of the last samples can overlap its prox / spectral analysis) and forms no gradient after it.
+    auto run_loop = [&](int n, int mode, bool last_of_run) {
         if (n <= 0) return;
         const bool graph = prm->use_graph && !c->profile && n >= 5;
         if (!graph) {
-            for (int i = 0; i < n; ++i) { mark_langevin = mark_last && i == n - 1; myula_step(); scalar(mode); }
+            for (int i = 0; i < n; ++i) {
+                const bool last = last_of_run && i == n - 1;
+                mark_langevin = last && out->X_last != nullptr;
+                unit(mode, !last);
+            }
             mark_langevin = false;
             return;
         }
-        if (mark_last) n -= 1;                                      // the last one runs eagerly below
-        myula_step(); scalar(mode);                                 // first iteration eagerly (sets kernel attributes)
+        if (last_of_run) n -= 1;                                    // the last one runs eagerly below
+        unit(mode, true);                                           // first iteration eagerly (sets kernel attributes)
         cudaGraph_t g = nullptr;
         cudaGraphExec_t ge = nullptr;
         const long long l0 = c->launches;
         SBD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         try {
-            myula_step(); scalar(mode);
+            unit(mode, true);
         } catch (...) {
             cudaStreamEndCapture(s, &g);
             if (g) cudaGraphDestroy(g);
@@ -1392,7 +1448,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
         SBD_CUDA(cudaGraphInstantiate(&ge, g, 0));
         for (int i = 1; i < n; ++i) SBD_CUDA(cudaGraphLaunch(ge, s));
         c->launches += per_iter * (n - 1);
-        if (mark_last) { mark_langevin = true; myula_step(); scalar(mode); mark_langevin = false; }
+        if (last_of_run) { mark_langevin = out->X_last != nullptr; unit(mode, false); mark_langevin = false; }
         SBD_CUDA(cudaStreamSynchronize(s));
         cudaGraphExecDestroy(ge);
         cudaGraphDestroy(g);
@@ -1401,6 +1457,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     // ---- warm-up (Guassian.m:67-93)
     analyse(c, nch);
     prox();                                                         // :76
+    gradient();                                                     // gradF(X_wu; initial parameters) for the first update
     run_loop(warmup - 1, 1, false);                                 // :78  for ii = 2:warmupSteps
     if (out->X_warm)
         SBD_CUDA(cudaMemcpyAsync(out->X_warm, c->X, sizeof(double) * nch * c->npix, cudaMemcpyDeviceToHost, s));
@@ -1415,7 +1472,10 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     SBD_CUDA(cudaEventRecord(evm, s));
     const long long launches0 = c->launches;
     const bool overlap_xlast = out->X_last != nullptr && samples >= 2;
-    run_loop(samples - 1, 2, overlap_xlast);                        // :158  for ii = 2:total_iter
+    // the timed region holds the whole work of samples-1 iterations: the gradient of the first one is formed here
+    // (again - the warm-up left one behind, outside the clock), the last one forms none after itself
+    if (samples >= 2) gradient();
+    run_loop(samples - 1, 2, true);                                 // :158  for ii = 2:total_iter
     SBD_CUDA(cudaEventRecord(ev1, s));
     if (overlap_xlast) {
         // X is final after the last Langevin kernel; what follows in that iteration only reads it.  One copy per

@@ -161,7 +161,7 @@ k_chamb_sweep(const double* __restrict__ g, const double* __restrict__ pxi,
     const int img = blockIdx.z;
     if (st[img].done) return;                       // this image already met the stop test (:131)
     const StripGeom s = strip_geom<V>(nx, ny, seg);
-    const double lambda = ctl->prox_lambda_theta, tau = ctl->tau;
+    const double lambda = ctl->prox_lambda_run, tau = ctl->tau;
     const double invlam = 1.0 / lambda;
     const size_t off = (size_t)img * img_stride;
     g += off; pxi += off; pyi += off; pxo += off; pyo += off;
@@ -282,7 +282,7 @@ k_chamb_out(const double* __restrict__ g, const double* __restrict__ px0,
     if (st[img].emitted) return;                    // the last fused block wrote f already (tv_multi.cuh)
     const StripGeom s = strip_geom<V>(nx, ny, seg);
     if (!s.warp_on) return;
-    const double lambda = ctl->prox_lambda_theta;
+    const double lambda = ctl->prox_lambda_run;
     const bool odd = st[img].buf != 0;
     const size_t off = (size_t)img * img_stride;
     const double* px = (odd ? px1 : px0) + off;
@@ -315,9 +315,19 @@ k_chamb_out(const double* __restrict__ g, const double* __restrict__ px0,
     }
 }
 
-__global__ void k_chamb_reset(ChambState* st, int n) {
+// start of a prox: clears the per-image state and takes the snapshot of lambda*theta the sweeps work from (the
+// scalar update of the same iteration may change ctl->prox_lambda_theta while the sweeps are still running)
+__global__ void k_chamb_reset(ChambState* st, int n, Control* ctl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) ctl->prox_lambda_run = ctl->prox_lambda_theta;
     if (i < n) { st[i].k = 0; st[i].done = 0; st[i].err = 0.0; st[i].counter = 0u; st[i].redo = 0; st[i].buf = 0; st[i].emitted = 0; }
+}
+
+// end of a main-loop prox: sweeps executed by chain 0 -> trace slot (SAPG `chambolle_iters`)
+__global__ void k_chamb_record(const ChambState* st, Control* ctl, int* trace, int n) {
+    const int k = ctl->prox_count;
+    if (k >= 0 && k < n) trace[k] = st[0].k;
+    ctl->prox_count = k + 1;
 }
 
 }  // namespace sbd

@@ -551,7 +551,7 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
         if (S->done) return;
         nlev = min(T, ctl->maxiter - S->k);
     }
-    const double lambda = ctl->prox_lambda_theta, tau = ctl->tau;
+    const double lambda = ctl->prox_lambda_run, tau = ctl->tau;
     const double invlam = 1.0 / lambda;
     const size_t off = (size_t)img * img_stride;
     g += off; pxi += off; pyi += off; pxo += off; pyo += off;
