@@ -100,7 +100,14 @@ k_rows2_fwd(const double* __restrict__ x, double2* __restrict__ spec, const __gr
     __syncthreads();
     stage_load<N, P::R2, P::R0 * P::R1, false>(tl, v, ssrc, tw);
     __syncthreads();
-    stage_store<N, P::R2, P::R0 * P::R1>(tl, v, sdst);
+    // The results of the last stage are Z[jb + 256 r] (jb = tl + m*TL, r < R2).  The split below pairs Z[k] with
+    // Z[N-k]: a thread's own k < N/2 are exactly its results with r < R2/2, so those stay in registers and only the
+    // upper half (r >= R2/2: the Z[N-k] of other threads, and Z[N/2]) goes through shared memory.
+    constexpr int RL = P::R2, ML = 16 / RL;
+#pragma unroll
+    for (int m = 0; m < ML; ++m)
+#pragma unroll
+        for (int r = RL / 2; r < RL; ++r) buf[swz(tl + m * TL + r * (N / RL))] = v[m * RL + r];
     __syncthreads();
     // split Z into the half spectra A (line q0) and B (line q0 + 1):  A[k] = (Z[k] + conj Z[N-k]) / 2,
     // B[k] = (Z[k] - conj Z[N-k]) / (2i); thread t takes k = t + j*TL, j = 0..7 (k < N/2), all reads first
@@ -108,8 +115,8 @@ k_rows2_fwd(const double* __restrict__ x, double2* __restrict__ spec, const __gr
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = tl + j * TL;
-        zk[j] = buf[swz(k)];
-        zm[j] = buf[swz((N - k) & (N - 1))];
+        zk[j] = v[(j % ML) * RL + j / ML];                          // = Z[k]: k = tl + (j % ML)*TL + 256*(j / ML)
+        zm[j] = (k == 0) ? zk[j] : buf[swz(N - k)];                 // Z[N-0] = Z[0]
     }
     double2 zn = make_double2(0.0, 0.0);
     if (tl == 0) zn = buf[swz(N / 2)];
@@ -170,13 +177,16 @@ k_rows2_inv(const double2* __restrict__ spec, double* __restrict__ out, const __
         B[j] = buf[slab(k, 1)];
     }
     __syncthreads();
+    // The first stage (radix 16) of thread t reads Z[t + r*N/16], r = 0..15: r < 8 are exactly the Z[k] this thread
+    // forms from its own slab entries - they stay in registers; only Z[N-k] (and Z[N/2]) go through shared memory.
+    double2 raw[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = tl + j * TL;
         if (k == 0) {
-            buf[swz(0)] = make_double2(A[j].x, B[j].x);             // C2R: imaginary parts of the real bins dropped
+            raw[j] = make_double2(A[j].x, B[j].x);                  // C2R: imaginary parts of the real bins dropped
         } else {
-            buf[swz(k)] = make_double2(A[j].x - B[j].y, A[j].y + B[j].x);
+            raw[j] = make_double2(A[j].x - B[j].y, A[j].y + B[j].x);
             buf[swz(N - k)] = make_double2(A[j].x + B[j].y, B[j].x - A[j].y);
         }
     }
@@ -187,7 +197,11 @@ k_rows2_inv(const double2* __restrict__ spec, double* __restrict__ out, const __
     auto sdst = [&](int p, double2 z) { buf[swz(p)] = z; };
     auto gdst = [&](int p, double2 z) { xo[p] = z.x; xo[N + p] = z.y; };
     double2 v[16];
-    stage_load<N, P::R0, 1, true>(tl, v, ssrc, tw);
+#pragma unroll
+    for (int r = 8; r < 16; ++r) raw[r] = buf[swz(tl + r * TL)];
+    int nraw = 0;
+    auto rsrc = [&](int) { return raw[nraw++]; };                    // stage_load asks for tl + r*N/16, r = 0..15, in order
+    stage_load<N, P::R0, 1, true>(tl, v, rsrc, tw);
     __syncthreads();
     stage_store<N, P::R0, 1>(tl, v, sdst);
     __syncthreads();
