@@ -195,7 +195,8 @@ typedef struct sbd_params {
     int32_t chain_offset;       /* global id of local chain 0 (Philox stream = id)         */
     int32_t total_chains;       /* chains over all ranks (>= n_chains)                     */
     int32_t post_mean;          /* 1: accumulate posterior mean of X for ii > burnIn       */
-    int32_t use_graph;          /* 1: replay each iteration from a CUDA graph              */
+    int32_t use_graph;          /* 1: replay each iteration from a CUDA graph; 0: eager launches;
+                                   -1: automatic (graph for small problems, rows*cols*n_chains <= 2^21) */
 } sbd_params;
 
 typedef struct sbd_traces {

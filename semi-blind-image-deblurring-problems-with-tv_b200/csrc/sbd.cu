@@ -129,6 +129,7 @@ struct sbd_ctx {
     cudaStream_t prox_stream = nullptr;                     // the prox of an iteration runs here, next to the analysis
     cudaEvent_t ev_fork = nullptr, ev_reset = nullptr, ev_join = nullptr;
     int opt_overlap = -1;                                   // -1 automatic (on unless profiling), 0 off
+    int opt_pdl = 1;                                        // programmatic dependent launch of the Chambolle kernels
     bool arm_ev_reset = false;
 
     // comm
@@ -361,12 +362,23 @@ void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const do
     constexpr int HL = (T + 1) & ~1, WO = 64 - 2 * HL;
     const int strips = (c->nx + WO - 1) / WO;
     dim3 grid((strips + TV_WARPS - 1) / TV_WARPS, c->cm_gy, batch);
+    // programmatic stream serialization: the launch is staged while the previous kernel of the stream still runs and
+    // starts the moment that one has completed (the kernel waits with griddepcontrol.wait before reading anything)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TV_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = c->opt_pdl ? 1 : 0;
+    const int nx = c->nx, ny = c->ny, seg = c->cm_seg;
+    const size_t npix = c->npix;
+    const Control* ctl = c->ctl;
     if (zero_in)
-        k_chamb_multi<T, PIPE, MINB, true, EMIT, ERRSUB><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
-                                                                                              strips, c->npix, c->ctl, c->chst, c->part_ch, redo, f);
+        SBD_CUDA(cudaLaunchKernelEx(&cfg, k_chamb_multi<T, PIPE, MINB, true, EMIT, ERRSUB>, g, pxi, pyi, pxo, pyo, nx, ny, seg, strips, npix,
+                                    ctl, c->chst, c->part_ch, redo, f));
     else
-        k_chamb_multi<T, PIPE, MINB, false, EMIT, ERRSUB><<<grid, TV_THREADS, 0, c->stream>>>(g, pxi, pyi, pxo, pyo, c->nx, c->ny, c->cm_seg,
-                                                                                               strips, c->npix, c->ctl, c->chst, c->part_ch, redo, f);
+        SBD_CUDA(cudaLaunchKernelEx(&cfg, k_chamb_multi<T, PIPE, MINB, false, EMIT, ERRSUB>, g, pxi, pyi, pxo, pyo, nx, ny, seg, strips, npix,
+                                    ctl, c->chst, c->part_ch, redo, f));
 }
 
 // zero_start: the dual pair starts from zero (px0/py0 are then neither read nor need to be cleared
@@ -659,6 +671,7 @@ int sbd_set_option(sbd_ctx* c, const char* name, int value) {
     else if (n == "chamb_plan33") c->opt_chamb_plan33 = value;
     else if (n == "chamb_errsub") c->opt_chamb_errsub = value;
     else if (n == "overlap") c->opt_overlap = value;
+    else if (n == "pdl") c->opt_pdl = value != 0;
     else if (n == "geom_chains") c->geom_total = std::max(value, 0);
     else { c->err = "sbd_set_option: unknown option '" + n + "'"; return SBD_E_INVALID; }
     c->geom_batch = -1;             // recomputed by the next call
@@ -747,6 +760,7 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
         SBD_CUDA(cudaEventCreateWithFlags(&c->ev_reset, cudaEventDisableTiming));
         SBD_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         if (const char* e = getenv("SBD_OVERLAP")) c->opt_overlap = atoi(e);
+        if (const char* e = getenv("SBD_PDL")) c->opt_pdl = atoi(e) != 0;
         {
             int dev = 0;
             SBD_CUDA(cudaGetDevice(&dev));
@@ -1419,7 +1433,9 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
     // that the copy of the last samples can overlap its prox / spectral analysis) and forms no gradient after it.
     auto run_loop = [&](int n, int mode, bool last_of_run) {
         if (n <= 0) return;
-        const bool graph = prm->use_graph && !c->profile && n >= 5;
+        // use_graph: 1 on, 0 off, -1 automatic = on for small problems, where the iteration is launch-bound
+        const bool want_graph = prm->use_graph > 0 || (prm->use_graph < 0 && (long long)c->npix * nch <= (1LL << 21));
+        const bool graph = want_graph && !c->profile && n >= 5;
         if (!graph) {
             for (int i = 0; i < n; ++i) {
                 const bool last = last_of_run && i == n - 1;

@@ -535,6 +535,12 @@ k_chamb_multi(const double* __restrict__ g, const double* __restrict__ pxi, cons
               size_t img_stride, const Control* __restrict__ ctl, ChambState* __restrict__ st,
               double* __restrict__ partials, int redo, double* __restrict__ f) {
     static_assert(EMIT == 0 || ((T + 1) & ~1) > T, "EMIT needs a spare pixel of lateral validity");
+    // Programmatic dependent launch (the launches of a prox follow each other on one stream, most of them no-ops or a
+    // few microseconds long on small images): wait here for the previous kernel of the stream to complete and flush
+    // before touching anything it wrote, then let the next launch be staged behind this one.  Both instructions are
+    // no-ops when the kernel was launched without the programmatic-serialization attribute.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     constexpr int HL = (T + 1) & ~1;
     constexpr int WO = 64 - 2 * HL;
     __shared__ double sm[T * 32];

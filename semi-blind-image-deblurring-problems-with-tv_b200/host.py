@@ -460,7 +460,7 @@ def make_params(model, op, c=None, n_chains=1, seed=1, chain_offset=0, total_cha
     p.d_scale = op["d_scale"]; p.d_exp = op["d_exp"]
     p.seed = int(seed); p.chain_offset = int(chain_offset)
     p.total_chains = int(total_chains if total_chains is not None else n_chains)
-    p.post_mean = int(bool(post_mean)); p.use_graph = int(op.get("use_graph", 0))
+    p.post_mean = int(bool(post_mean)); p.use_graph = int(op.get("use_graph", -1))       # -1: automatic
     return p
 
 

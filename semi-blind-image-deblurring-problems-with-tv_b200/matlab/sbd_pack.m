@@ -48,5 +48,7 @@ end
 P.sigma2_init = op.sigma_init; P.sigma2_min = op.sigma_min; P.sigma2_max = op.sigma_max; P.fix_sigma = op.fix_sigma;
 P.d_scale = op.d_scale; P.d_exp = op.d_exp; P.seed = 1;
 if isfield(op, 'seed'), P.seed = op.seed; end
+P.use_graph = -1;                                                    % automatic: CUDA-graph replay for small images
+if isfield(op, 'use_graph'), P.use_graph = op.use_graph; end
 r2res = names;
 end

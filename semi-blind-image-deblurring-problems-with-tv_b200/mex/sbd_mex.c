@@ -212,6 +212,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         p.err_psf_lag = (int)field(P, "err_psf_lag", 0, 0);
         p.d_scale = field(P, "d_scale", 1, 0); p.d_exp = field(P, "d_exp", 1, 0);
         p.seed = (uint64_t)field(P, "seed", 0, 1); p.chain_offset = 0; p.total_chains = p.n_chains;
+        p.use_graph = (int)field(P, "use_graph", 0, -1);            /* -1: automatic (CUDA graph for small problems) */
         c = get_ctx(rows, cols, (int)mxGetScalar(prhs[5]), (int)mxGetScalar(prhs[4]), mxGetScalar(prhs[6]), p.n_chains);
         nm = p.samples - p.burnIn; if (nm < 0) nm = 0;
         r = mxCreateStructMatrix(1, 1, (int)(sizeof names / sizeof names[0]), names);

@@ -68,6 +68,7 @@ def make_sbd_mex(sbd):
             for i in range(2):
                 p.fix_psi[i] = int(v[i] != 0) if i < v.size else 0
             p.seed = int(_s(P["seed"])); p.chain_offset = 0; p.total_chains = p.n_chains
+            p.use_graph = int(_s(P["use_graph"])) if "use_graph" in P else -1
             eng = H.engine_for(y.shape, t, model, phi, max_batch=p.n_chains)
             if noise is not None:           # MATLAB side hands [rows, cols*draws]; the tests pass a 4-D numpy tape
                 noise = np.asarray(noise)

@@ -175,8 +175,10 @@ def test_sapg_cuda_graph_mode_is_identical(sbd, O, cman):
     """use_graph replays the captured iteration: trajectories must be bit-identical to eager launches."""
     x = cman[96:160, 64:128]
     tape, (y, op, c) = _setup(O, 0, x, samples=24, warmup=9, burnIn=12, fix_w1=0, fix_w2=0)
-    _, _, _, _, a = sbd.SAPG_algorithm_Guassian(y, op, c, n_chains=2, seed=5)
+    _, _, _, _, a = sbd.SAPG_algorithm_Guassian(y, dict(op, use_graph=0), c, n_chains=2, seed=5)
     _, _, _, _, b = sbd.SAPG_algorithm_Guassian(y, dict(op, use_graph=1), c, n_chains=2, seed=5)
+    _, _, _, _, d = sbd.SAPG_algorithm_Guassian(y, op, c, n_chains=2, seed=5)          # default: automatic
     for k in ("thetas", "w1s", "w2s", "sigmas", "logPiTraceX", "logPiTrace_WU", "gXTrace", "grad_w1"):
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(a["Xlast_sample"], b["Xlast_sample"])
+    assert np.array_equal(a["Xlast_sample"], d["Xlast_sample"]) and np.array_equal(a["thetas"], d["thetas"])

@@ -63,7 +63,7 @@ def test_config0_gaussian_cman_256(sbd, O, cman):
     tape.record = True
     th, w1, w2, s2, r = O.sapg.SAPG_algorithm_Guassian(y, op, c, tape)
     noise = np.stack(tape.tape)[:, None]
-    gth, gw1, gw2, gs2, g = sbd.SAPG_algorithm_Guassian(y, op, c, noise=noise)
+    gth, gw1, gw2, gs2, g = sbd.SAPG_algorithm_Guassian(y, dict(op, use_graph=0), c, noise=noise)
     _traj(g, r, COMMON + ["w1s", "w2s", "grad_theta", "grad_w1", "grad_w2", "grad_sigma", "mean_thetas", "mean_w1s"])
     assert rel(g["Xlast_sample"], r["Xlast_sample"]) < TRAJ_TOL
     for a, b in ((gth, th), (gw1, w1), (gw2, w2), (gs2, s2)):
