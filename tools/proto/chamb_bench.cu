@@ -5,6 +5,12 @@
 #ifndef HARNESS_ERRSUB
 #define HARNESS_ERRSUB false
 #endif
+#ifndef HARNESS_T
+#define HARNESS_T 4
+#endif
+#ifndef HARNESS_MINB
+#define HARNESS_MINB 3
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -25,10 +31,10 @@ int main(int argc, char** argv) {
     for (int b = 0; b < batch; ++b) CK(cudaMemcpy(g + b * npix, h.data(), npix * 8, cudaMemcpyHostToDevice));
     CK(cudaMemset(px0, 0, tot * 8)); CK(cudaMemset(py0, 0, tot * 8));
     Control hc; memset(&hc, 0, sizeof hc);
-    hc.prox_lambda_theta = 0.3; hc.tau = 0.249; hc.tol = 0.0; hc.maxiter = 1 << 30;
+    hc.prox_lambda_theta = 0.3; hc.prox_lambda_run = 0.3; hc.tau = 0.249; hc.tol = 0.0; hc.maxiter = 1 << 30;
     Control* ctl; CK(cudaMalloc(&ctl, sizeof hc)); CK(cudaMemcpy(ctl, &hc, sizeof hc, cudaMemcpyHostToDevice));
     ChambState* st; CK(cudaMalloc(&st, sizeof(ChambState) * batch)); CK(cudaMemset(st, 0, sizeof(ChambState) * batch));
-    constexpr int T = 4, HL = 4, WO = 64 - 2 * HL;
+    constexpr int T = HARNESS_T, HL = HARNESS_T, WO = 64 - 2 * HL;
     const int strips = (n + WO - 1) / WO;
     dim3 grid((strips + TV_WARPS - 1) / TV_WARPS, (n + seg - 1) / seg, batch);
     CK(cudaMalloc(&part, sizeof(double) * T * grid.x * grid.y * batch));
@@ -36,7 +42,7 @@ int main(int argc, char** argv) {
     auto run = [&](int i) {
         const double* pxi = (i & 1) ? px1 : px0; const double* pyi = (i & 1) ? py1 : py0;
         double* pxo = (i & 1) ? px0 : px1; double* pyo = (i & 1) ? py0 : py1;
-        k_chamb_multi<4, false, 3, false, 0, HARNESS_ERRSUB><<<grid, TV_THREADS>>>(g, pxi, pyi, pxo, pyo, n, n, seg, strips, npix, ctl, st, part, 0, nullptr);
+        k_chamb_multi<HARNESS_T, false, HARNESS_MINB, false, 0, HARNESS_ERRSUB><<<grid, TV_THREADS>>>(g, pxi, pyi, pxo, pyo, n, n, seg, strips, npix, ctl, st, part, 0, nullptr);
     };
     for (int i = 0; i < 4; ++i) run(i);
     CK(cudaDeviceSynchronize());
@@ -49,7 +55,7 @@ int main(int argc, char** argv) {
     double chk = 0; std::vector<double> o(1024);
     CK(cudaMemcpy(o.data(), px0 + npix / 2 + 77, 1024 * 8, cudaMemcpyDeviceToHost));
     for (double v : o) chk += v;
-    printf("batch %d seg %d: %.4f ms per 4-sweep launch (%.4f ms per sweep of 8 chains-equivalent)  k=%d err=%.10e chk=%.12e\n",
-           batch, seg, ms / reps, ms / reps / 4 * 8 / batch, hs[0].k, hs[0].err, chk);
+    printf("batch %d seg %d: %.4f ms per T-sweep launch (%.4f ms per sweep of 8 chains-equivalent)  k=%d err=%.10e chk=%.12e\n",
+           batch, seg, ms / reps, ms / reps / T * 8 / batch, hs[0].k, hs[0].err, chk);
     return 0;
 }
