@@ -277,12 +277,17 @@ const char* sbd_phase_name(int i);
  *   "chamb_errsub" sampled stop test (the sum of err_k^2 over a subset of the rows already proves err_k > tol;
  *                  exact fallback otherwise; same k, p and f): 1 whenever the caller does not ask for the value
  *                  of err (SAPG, sbd_tvprox_dev with err == NULL), 0 never, -1 automatic (large problems only)
+ *   "chamb_coop"   the whole prox (all sweeps, stop test, f) as ONE cooperative launch, one warp per (row, 64-pixel
+ *                  strip), blocks of an image synchronised by a barrier per sweep (tv_coop.cuh): 1 whenever the grid
+ *                  fits the device, 0 never, -1 automatic (rows*cols*chains <= 2^21 and none of the options above set)
  *   "tv_seg"       rows per segment of the TVnorm / single-sweep / output kernels
  *   "geom_chains"  derive the geometry from this many chains instead of the batch
  * sbd_get_geometry: out = {levels, chamb_seg, chamb_grid_x, chamb_grid_y,
- *                          tv_seg, tv_grid_x, tv_grid_y, rows_line_pairs}
+ *                          tv_seg, tv_grid_x, tv_grid_y, rows_line_pairs,
+ *                          coop_blocks_per_image, coop_units_per_warp}   (the last two 0: the prox of `batch` images
+ *                          runs the fused kernels)
  * ---------------------------------------------------------------------- */
-#define SBD_N_GEOM 8
+#define SBD_N_GEOM 10
 int sbd_set_option(sbd_ctx* ctx, const char* name, int value);
 int sbd_get_geometry(sbd_ctx* ctx, int batch, int out[SBD_N_GEOM]);
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsbd.so")
 
 SBD_N_PHASES = 8
-SBD_N_GEOM = 8
+SBD_N_GEOM = 10
 SBD_NCCL_ID_BYTES = 128
 
 c_double_p = C.POINTER(C.c_double)

@@ -8,6 +8,7 @@
 #include "psf.cuh"
 #include "tv.cuh"
 #include "tv_multi.cuh"
+#include "tv_coop.cuh"
 #include "fft.cuh"
 #include "fft2.cuh"
 #include "sapg.cuh"
@@ -130,6 +131,9 @@ struct sbd_ctx {
     cudaEvent_t ev_fork = nullptr, ev_reset = nullptr, ev_join = nullptr;
     int opt_overlap = -1;                                   // -1 automatic (on unless profiling), 0 off
     int opt_pdl = 1;                                        // programmatic dependent launch of the Chambolle kernels
+    int opt_chamb_coop = -1;                                // cooperative single-launch prox (tv_coop.cuh): -1 auto (small problems), 0 never, 1 whenever it fits
+    int cc_cap = 0;                                         // co-resident blocks of k_chamb_coop on this device
+    unsigned int* cc_bar = nullptr;                         // its per-image barrier counters
     bool arm_ev_reset = false;
 
     // comm
@@ -181,7 +185,7 @@ void make_twiddles(int n, double2* d, cudaStream_t s) {
 void free_ws(sbd_ctx* c) {
     dfree(c->X); dfree(c->P); dfree(c->Gf); dfree(c->px0); dfree(c->py0); dfree(c->px1); dfree(c->py1);
     dfree(c->S1); dfree(c->S2);
-    dfree(c->chst); dfree(c->cnt_tv); dfree(c->cnt_col); dfree(c->cnt_sq); dfree(c->stats);
+    dfree(c->cc_bar); dfree(c->chst); dfree(c->cnt_tv); dfree(c->cnt_col); dfree(c->cnt_sq); dfree(c->stats);
     dfree(c->part_tv); dfree(c->part_ch); dfree(c->part_col); dfree(c->part_sq);
     c->ws_batch = 0;
 }
@@ -281,6 +285,8 @@ void ensure_ws(sbd_ctx* c, int batch) {
         if (c->v2) { c->tm_S1 = make_spec_tmap(c, c->S1, batch); c->tm_S2 = make_spec_tmap(c, c->S2, batch); }
     }
     c->chst = dalloc<ChambState>(batch);
+    c->cc_bar = dalloc<unsigned int>(batch);
+    SBD_CUDA(cudaMemsetAsync(c->cc_bar, 0, sizeof(unsigned int) * batch, c->stream));
     c->cnt_tv = dalloc<unsigned int>(batch); c->cnt_col = dalloc<unsigned int>(batch); c->cnt_sq = dalloc<unsigned int>(batch);
     c->stats = dalloc<double>((size_t)batch * NSTAT);
     SBD_CUDA(cudaMemsetAsync(c->cnt_tv, 0, sizeof(unsigned int) * batch, c->stream));
@@ -381,16 +387,64 @@ void chamb_multi_launch(sbd_ctx* c, const double* g, const double* pxi, const do
                                     ctl, c->chst, c->part_ch, redo, f));
 }
 
+// Does the prox of `batch` images run as the cooperative single-launch kernel, and with which partition?  The partition
+// (blocks per image, units per warp) fixes the order of the err_k partial sums, so like the rest of the launch geometry it
+// is a function of the TOTAL chain count, not of the chains on this rank.
+bool coop_plan(sbd_ctx* c, int batch, int& bpi, int& upw) {
+    if (c->opt_chamb_coop == 0 || c->nx % 2 != 0 || c->nx < 2 || c->ny < 2) return false;
+    const int total = std::max(batch, c->geom_total);
+    const long long units = (long long)c->ny * ((c->nx + 63) / 64);
+    if (c->opt_chamb_coop < 0) {
+        // automatic: small problems only (measured with tools/coop_crossover.py: ahead up to 2^21 pixels x chains - 1.7x at
+        // 256^2 x 1, 1.55x at 512^2 x 8, 1.1x at 1024^2 x 2 - behind from 2^22), and never when an option addresses the
+        // fused kernel explicitly
+        if ((long long)c->npix * total > (1LL << 21)) return false;
+        if (c->opt_chamb_seg > 0 || c->opt_chamb_T > 0 || c->opt_chamb_errsub >= 0 || c->opt_chamb_emit >= 0 || c->opt_chamb_plan33 >= 0) return false;
+    }
+    if (!c->cc_cap) {
+        int per_sm = 0;
+        SBD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chamb_coop, CC_THREADS, 0));
+        c->cc_cap = std::max(1, per_sm) * c->sm_count;
+    }
+    for (upw = 1; upw <= 256; upw *= 2) {
+        bpi = (int)((units + (long long)CC_WARPS * upw - 1) / ((long long)CC_WARPS * upw));
+        if ((long long)bpi * total <= c->cc_cap) return true;
+    }
+    return false;
+}
+
 // zero_start: the dual pair starts from zero (px0/py0 are then neither read nor need to be cleared
 // when the fused kernel runs; the single-sweep path clears them itself)
 // want_err == false: the caller never reads the VALUE of err_k (only the sweep count), which allows the sampled stop
 // test of tv_multi.cuh (ERRSUB) on large problems: same k, same p, same f, 12 % fewer fp64 instructions per sweep
-void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, bool zero_start, bool keep_duals = true,
-               bool want_err = true) {
+// trace/ntrace: where the sweep count of chain 0 is recorded at the end of a main-loop prox (k_chamb_record); the
+// cooperative kernel does that itself, every other path leaves it to the caller - returns true when it was recorded
+bool chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, bool zero_start, bool keep_duals = true,
+               bool want_err = true, int* trace = nullptr, int ntrace = 0) {
     SBD_REQUIRE(maxiter >= 1, SBD_E_INVALID, "chambolle: maxiter must be >= 1");       // the block plan below relies on it
-    k_chamb_reset<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->chst, batch, c->ctl);
+    k_chamb_reset<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->chst, batch, c->ctl, c->cc_bar);
     LAUNCH_CHECK(c);
     if (c->arm_ev_reset) SBD_CUDA(cudaEventRecord(c->ev_reset, c->stream));     // the lambda*theta snapshot is taken
+    {
+        int bpi = 0, upw = 0;
+        if (coop_plan(c, batch, bpi, upw)) {
+            // small problem: all sweeps, the stop test and f = g - lambda div p in ONE cooperative launch (tv_coop.cuh)
+            PhaseTimer pt2(c, 2);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(batch * bpi)); cfg.blockDim = dim3(CC_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            const int nx = c->nx, ny = c->ny, zs = zero_start ? 1 : 0;
+            const size_t npix = c->npix;
+            const Control* ctl = c->ctl;
+            SBD_CUDA(cudaLaunchKernelEx(&cfg, k_chamb_coop, g, c->px0, c->py0, c->px1, c->py1, f, nx, ny, npix, bpi, upw, zs, maxiter,
+                                        ctl, c->chst, c->part_ch, c->cc_bar, c->ctl, trace, ntrace));
+            LAUNCH_CHECK(c);
+            return trace != nullptr;
+        }
+    }
     dim3 grid(c->tv_gx, c->tv_gy, batch);
     PhaseTimer* pt = new PhaseTimer(c, 2);
     if (c->cmT > 1) {
@@ -469,6 +523,7 @@ void chambolle(sbd_ctx* c, const double* g, double* f, int batch, int maxiter, b
     else
         k_chamb_out<1><<<grid, TV_THREADS, 0, c->stream>>>(g, c->px0, c->py0, c->px1, c->py1, f, c->nx, c->ny, c->tv_seg, c->npix, c->ctl, c->chst);
     LAUNCH_CHECK(c);
+    return false;
 }
 
 template <typename K>
@@ -672,6 +727,7 @@ int sbd_set_option(sbd_ctx* c, const char* name, int value) {
     else if (n == "chamb_errsub") c->opt_chamb_errsub = value;
     else if (n == "overlap") c->opt_overlap = value;
     else if (n == "pdl") c->opt_pdl = value != 0;
+    else if (n == "chamb_coop") c->opt_chamb_coop = value;
     else if (n == "geom_chains") c->geom_total = std::max(value, 0);
     else { c->err = "sbd_set_option: unknown option '" + n + "'"; return SBD_E_INVALID; }
     c->geom_batch = -1;             // recomputed by the next call
@@ -683,6 +739,11 @@ int sbd_get_geometry(sbd_ctx* c, int batch, int out[SBD_N_GEOM]) {
     set_geometry(c, batch);
     out[0] = c->cmT; out[1] = c->cm_seg; out[2] = c->cm_gx; out[3] = c->cm_gy;
     out[4] = c->tv_seg; out[5] = c->tv_gx; out[6] = c->tv_gy; out[7] = c->rowsLP;
+    try {
+        int bpi = 0, upw = 0;
+        const bool coop = coop_plan(c, batch, bpi, upw);
+        out[8] = coop ? bpi : 0; out[9] = coop ? upw : 0;
+    } catch (const Error& e) { c->err = e.msg; return e.code; }
     return SBD_OK;
 }
 
@@ -761,6 +822,7 @@ int sbd_create(sbd_ctx** out, int rows, int cols, int psf_size, int model, doubl
         SBD_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         if (const char* e = getenv("SBD_OVERLAP")) c->opt_overlap = atoi(e);
         if (const char* e = getenv("SBD_PDL")) c->opt_pdl = atoi(e) != 0;
+        if (const char* e = getenv("SBD_CHAMB_COOP")) c->opt_chamb_coop = atoi(e);
         {
             int dev = 0;
             SBD_CUDA(cudaGetDevice(&dev));
@@ -1367,9 +1429,12 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
 
     const double* gstats = nullptr;
     bool mark_langevin = false;         // set for the last iteration: X is final once its Langevin kernel has run
-    auto prox = [&]() {
+    auto prox = [&](int mode) {
         PhaseTimer pt(c, 3);
-        chambolle(c, c->X, c->P, nch, prm->chambolle_maxiter, true, false, false);    // zero start: chambolle_prox_TV_stop.m:68-69
+        const bool rec = mode == 2;         // main loop: sweeps of chain 0 -> `chambolle_iters`
+        const bool done = chambolle(c, c->X, c->P, nch, prm->chambolle_maxiter, true, false, false,       // zero start: chambolle_prox_TV_stop.m:68-69
+                                    rec ? dt.t.chamb_k : nullptr, samples);
+        if (rec && !done) { k_chamb_record<<<1, 1, 0, c->stream>>>(c->chst, c->ctl, dt.t.chamb_k, samples); LAUNCH_CHECK(c); }
     };
     // gradF with the CURRENT parameters from the spectrum of the current sample (S1): what the next Langevin update uses
     auto gradient = [&]() {
@@ -1405,14 +1470,12 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
             {
                 StreamScope sc(c, c->prox_stream);
                 c->arm_ev_reset = true;
-                try { prox(); } catch (...) { c->arm_ev_reset = false; throw; }
+                try { prox(mode); } catch (...) { c->arm_ev_reset = false; throw; }
                 c->arm_ev_reset = false;
-                if (mode == 2) { k_chamb_record<<<1, 1, 0, c->stream>>>(c->chst, c->ctl, dt.t.chamb_k, samples); LAUNCH_CHECK(c); }
                 SBD_CUDA(cudaEventRecord(c->ev_join, c->stream));
             }
         } else {
-            prox();
-            if (mode == 2) { k_chamb_record<<<1, 1, 0, s>>>(c->chst, c->ctl, dt.t.chamb_k, samples); LAUNCH_CHECK(c); }
+            prox(mode);
         }
         analyse(c, nch);
         if (d_xtrue) {
@@ -1472,7 +1535,7 @@ void sapg_run_impl(sbd_ctx* c, const double* d_y, const double* d_X0, const doub
 
     // ---- warm-up (Guassian.m:67-93)
     analyse(c, nch);
-    prox();                                                         // :76
+    prox(1);                                                        // :76
     gradient();                                                     // gradF(X_wu; initial parameters) for the first update
     run_loop(warmup - 1, 1, false);                                 // :78  for ii = 2:warmupSteps
     if (out->X_warm)

@@ -317,9 +317,10 @@ k_chamb_out(const double* __restrict__ g, const double* __restrict__ px0,
 
 // start of a prox: clears the per-image state and takes the snapshot of lambda*theta the sweeps work from (the
 // scalar update of the same iteration may change ctl->prox_lambda_theta while the sweeps are still running)
-__global__ void k_chamb_reset(ChambState* st, int n, Control* ctl) {
+__global__ void k_chamb_reset(ChambState* st, int n, Control* ctl, unsigned int* bar) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) ctl->prox_lambda_run = ctl->prox_lambda_theta;
+    if (i < n) bar[i] = 0u;                         // barrier counters of the cooperative kernel (tv_coop.cuh)
     if (i < n) { st[i].k = 0; st[i].done = 0; st[i].err = 0.0; st[i].counter = 0u; st[i].redo = 0; st[i].buf = 0; st[i].emitted = 0; }
 }
 

@@ -93,7 +93,8 @@ class Engine:
         """dict of the launch geometry libsbd would use for a batch of `batch` images."""
         out = (C.c_int * SBD_N_GEOM)()
         self._check(lib.sbd_get_geometry(self._h, int(batch), out))
-        keys = ("levels", "chamb_seg", "chamb_grid_x", "chamb_grid_y", "tv_seg", "tv_grid_x", "tv_grid_y", "rows_line_pairs")
+        keys = ("levels", "chamb_seg", "chamb_grid_x", "chamb_grid_y", "tv_seg", "tv_grid_x", "tv_grid_y", "rows_line_pairs",
+                "coop_blocks_per_image", "coop_units_per_warp")
         return dict(zip(keys, list(out)))
 
     def phase_times(self):

@@ -134,8 +134,9 @@ def test_batch_mixed_stops_long_segments(sbd, O):
 @pytest.mark.parametrize("n,segmin", [(1024, 8), (2048, 16)])
 def test_large_single_image(sbd, O, n, segmin):
     eng = sbd.Engine(n, n, 1, 0, 0.0, max_batch=1)
+    eng.set_option("chamb_coop", 0)         # the fused kernels (one 1024^2 image would otherwise take the cooperative prox)
     geo = eng.geometry(1)
-    assert geo["levels"] == 4 and geo["chamb_seg"] >= segmin, geo
+    assert geo["levels"] == 4 and geo["chamb_seg"] >= segmin and geo["coop_blocks_per_image"] == 0, geo
     g = natural((n, n), n)
     for lam, K in ((0.1, 25), (2.0, 20), (1e-3, 25)):
         check(eng, O, g, lam, K)
@@ -305,7 +306,7 @@ def test_set_option_rejects_unknown_names(sbd):
     eng = sbd.Engine(64, 64, 1, 0, 0.0, max_batch=1)
     with pytest.raises(SbdError):
         eng.set_option("no_such_option", 1)
-    for name in ("chamb_seg", "chamb_levels", "chamb_emit", "chamb_plan33", "chamb_errsub", "tv_seg", "geom_chains"):
+    for name in ("chamb_seg", "chamb_levels", "chamb_emit", "chamb_plan33", "chamb_errsub", "chamb_coop", "tv_seg", "geom_chains"):
         eng.set_option(name, -1 if name != "geom_chains" else 0)
     assert eng.geometry(1)["levels"] == 4
     eng.close()

@@ -25,10 +25,11 @@ def main():
     ap.add_argument("--chains", type=int, default=1)
     ap.add_argument("--cpu-iters", type=int, default=20)
     ap.add_argument("--graph", type=int, default=0)
+    ap.add_argument("--image", default="cman", help="cman (256x256) or boat (512x512)")
     a = ap.parse_args()
     import sbd_b200
     from sbd_b200 import host as H
-    x = np.load(os.path.join(ROOT, "tests", "golden", "cman_u8.npy")).astype(np.float64)
+    x = np.load(os.path.join(ROOT, "tests", "golden", a.image + "_u8.npy")).astype(np.float64)
     n = x.shape[0]
     eng = sbd_b200.Engine(n, n, 7, H.GAUSSIAN, 0.0, a.chains, 0)
     rng = np.random.default_rng(1)
