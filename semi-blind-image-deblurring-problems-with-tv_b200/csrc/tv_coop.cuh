@@ -15,6 +15,22 @@
 
 namespace sbd {
 
+// -DSBD_CC_TIMING (tools/proto/coop_bench.cu): thread 0 of block 0 adds up clock64 intervals of the phases of a sweep.
+// Measured on B200, 256^2, one image, cycles per sweep: operands of the sweep arrive (L2, written by other SMs) 1625,
+// level step 707, stores issued 178, block sum (incl. waiting for the block's slowest warp) 1111, release (MEMBAR.GPU
+// + count) 988, wait for the other blocks 854, closing barrier 358 = 5800 cycles, 2.9 us.  Variants that lost:
+// per-warp arrival without the block sum (eight fences per block instead of one: 82 vs 78 us per prox), relaxed
+// polling instead of acquire (no change: the L1 invalidation is not what delays the operands).
+#ifdef SBD_CC_TIMING
+__device__ long long cc_timing[8];
+#define CC_T(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t__ = clock64(); cc_timing[i] += t__ - cc_t0; cc_t0 = t__; } } while (0)
+// the same, but the clock is read only once `val` is available
+#define CC_TD(i, val) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t__; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t__) : "d"(val) : "memory"); cc_timing[i] += t__ - cc_t0; cc_t0 = t__; } } while (0)
+#else
+#define CC_T(i) do { } while (0)
+#define CC_TD(i, val) do { } while (0)
+#endif
+
 constexpr int CC_WARPS = 8;
 constexpr int CC_THREADS = CC_WARPS * 32;
 
@@ -55,6 +71,9 @@ k_chamb_coop(const double* __restrict__ g, double* px0, double* py0, double* px1
 
     int k = 0;
     double err = 0.0;
+#ifdef SBD_CC_TIMING
+    long long cc_t0 = clock64();
+#endif
     for (int s = 1; s <= maxiter; ++s) {
         const double* pxi = ((s - 1) & 1) ? px1 : px0;
         const double* pyi = ((s - 1) & 1) ? py1 : py0;
@@ -95,6 +114,7 @@ k_chamb_coop(const double* __restrict__ g, double* px0, double* py0, double* px1
                     if (edgeR) { pxR = __ldcg(pxi + r + 2); pyR = __ldcg(pyi + r + 2); if (up) pyuR = __ldcg(pyi + r - nx + 2); }
                 }
             }
+            CC_TD(5, P.x + Q.y + Qu.x + Pn.y + Qn.x + G.x + Gn.y);        // operands have arrived
             // u on row j (:152-159, :124)
             CcRow h;
             h.px[0] = P.x; h.px[1] = P.y; h.py[0] = Q.x; h.py[1] = Q.y;
@@ -133,12 +153,14 @@ k_chamb_coop(const double* __restrict__ g, double* px0, double* py0, double* px1
             double opx[2], opy[2], ex[2], ey[2];
             cm_core<2>(upx, un, h, tau, opx, opy, ex, ey, K);
             const double e = fma(ex[1], ex[1], fma(ey[1], ey[1], fma(ex[0], ex[0], ey[0] * ey[0])));      // :128
+            CC_TD(6, e + opx[1] + opy[0]);                                     // level step done
             if (on) {
                 acc[0] += e;
                 *reinterpret_cast<double2*>(pxo + r) = make_double2(opx[0], opx[1]);
                 *reinterpret_cast<double2*>(pyo + r) = make_double2(opy[0], opy[1]);
             }
         }
+        CC_T(0);                                             // stores issued
         if (warp == 0 && s > 1) {
             const double tot = warp_sum(psum);               // same order in every block of the image (warp_sum_partials)
             if (lane == 0) s_err = sqrt(tot);                                                           // :128
@@ -148,16 +170,20 @@ k_chamb_coop(const double* __restrict__ g, double* px0, double* py0, double* px1
             err = s_err;                                                                                // err_(s-1)
             if (!(err > tol)) break;                                                                    // :131, k = s-1
         }
+        CC_T(1);                                             // block sum
         double* part = partials + (size_t)(s & 1) * gridDim.x + (size_t)z * bpi;
         if (threadIdx.x == 0) {
             part[b] = acc[0];
             // barrier between the blocks of this image: the release orders the block's stores (which happen before it
             // through the __syncthreads inside block_sum and this thread's program order) before the count
             cc_red_release(mybar, 1u);
+            CC_T(2);                                         // release (fence + count)
             const unsigned int target = (unsigned int)s * (unsigned int)bpi;
             while (cc_ld_acquire(mybar) < target) { }
+            CC_T(3);                                         // wait for the other blocks
         }
         __syncthreads();
+        CC_T(4);
         k = s;                                                                                          // :121
     }
     if (k == maxiter) {

@@ -58,6 +58,8 @@ def main():
            "theta_EB": th, "w1_EB": w1, "w2_EB": w2, "sigma2_EB": s2, "true": {"w1": 0.4, "w2": 0.3, "sigma2": sigma ** 2},
            "psnr_y": oracle.metrics.PSNR(x, y), "psnr_mmse": oracle.metrics.PSNR(x, xm),
            "chambolle_sweeps_mean": float(np.mean(r["chambolle_iters"][1:]))}
+    if os.environ.get("SBD_PROFILE"):
+        out["phase_ms_calls"] = {k_: (round(v_[0], 3), v_[1]) for k_, v_ in eng.phase_times().items()}
     if a.cpu_iters > 0:
         import scipy.fft
         from oracle import operators as OP
