@@ -20,7 +20,8 @@ namespace sbd {
 // level step 707, stores issued 178, block sum (incl. waiting for the block's slowest warp) 1111, release (MEMBAR.GPU
 // + count) 988, wait for the other blocks 854, closing barrier 358 = 5800 cycles, 2.9 us.  Variants that lost:
 // per-warp arrival without the block sum (eight fences per block instead of one: 82 vs 78 us per prox), relaxed
-// polling instead of acquire (no change: the L1 invalidation is not what delays the operands).
+// polling instead of acquire (no change: the L1 invalidation is not what delays the operands), 3 or 4 resident blocks
+// per SM (80 / 82 us), 4 / 16 / 32 warps per block (84 / 94 / 228 us).
 #ifdef SBD_CC_TIMING
 __device__ long long cc_timing[8];
 #define CC_T(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t__ = clock64(); cc_timing[i] += t__ - cc_t0; cc_t0 = t__; } } while (0)
@@ -31,7 +32,10 @@ __device__ long long cc_timing[8];
 #define CC_TD(i, val) do { } while (0)
 #endif
 
-constexpr int CC_WARPS = 8;
+#ifndef SBD_CC_WARPS
+#define SBD_CC_WARPS 8
+#endif
+constexpr int CC_WARPS = SBD_CC_WARPS;
 constexpr int CC_THREADS = CC_WARPS * 32;
 
 __device__ __forceinline__ unsigned int cc_ld_acquire(const unsigned int* p) {
