@@ -74,3 +74,18 @@ def test_chambolle_loop_mix_matches_the_issue_model(sass):
     # the variant with the full err sums carries 64 more fp64 instructions per trip
     full = one(sass, "k_chamb_multiILi4ELb0ELi3ELb0ELi0ELb0E")
     assert full.count("DFMA") > body.count("DFMA")
+
+
+def test_cooperative_prox_kernel(sass):
+    """tv_coop.cuh: the per-sweep barrier is one gpu-scope fence + one reduction per block and an acquire poll; the
+    operands written by other SMs are read past L1; the level step keeps the MUFU-seeded root / reciprocal (two of each
+    for the two pixels of a lane, once); nothing spills under the two-blocks-per-SM bound."""
+    body = one(sass, "k_chamb_coop")
+    assert body.count("MEMBAR.ALL.GPU") == 1 and body.count("REDG.E.ADD.STRONG.GPU") == 1
+    assert "LDG.E.STRONG.GPU" in body and "CCTL.IVALL" in body                       # the polling load of the barrier
+    assert len(re.findall(r"LDG\.E\.(64|128)\.STRONG\.GPU", body)) >= 10                # dual pair read from L2
+    assert body.count("MUFU.RSQ64H") >= 2 and body.count("MUFU.RCP64H") >= 2       # + the two sqrt of err_k and 1 / lambda
+    assert not re.search(r"\b(LDL|STL)\b", body)
+    res = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True, check=True).stdout
+    m = re.search(r"k_chamb_coop[^\n]*\n\s*REG:(\d+)", res)
+    assert m and int(m.group(1)) <= 128
