@@ -21,7 +21,9 @@ namespace sbd {
 // + count) 988, wait for the other blocks 854, closing barrier 358 = 5800 cycles, 2.9 us.  Variants that lost:
 // per-warp arrival without the block sum (eight fences per block instead of one: 82 vs 78 us per prox), relaxed
 // polling instead of acquire (no change: the L1 invalidation is not what delays the operands), 3 or 4 resident blocks
-// per SM (80 / 82 us), 4 / 16 / 32 warps per block (84 / 94 / 228 us).
+// per SM (80 / 82 us), 4 / 16 / 32 warps per block (84 / 94 / 228 us), the operands of a warp's next unit fetched
+// while the current one is worked on (upw > 1; 512^2: 125 vs 116 us - 128 registers, and the other resident warps
+// already cover the wait).
 #ifdef SBD_CC_TIMING
 __device__ long long cc_timing[8];
 #define CC_T(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t__ = clock64(); cc_timing[i] += t__ - cc_t0; cc_t0 = t__; } } while (0)
