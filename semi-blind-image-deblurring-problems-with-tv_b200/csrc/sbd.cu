@@ -247,7 +247,9 @@ void set_geometry(sbd_ctx* c, int batch_local) {
         int sg = 128;
         // small problems are latency-bound (one warp per SM): shorter segments trade redundant halo rows for
         // parallelism (256^2, one chain: 4-row segments are 10 % faster than 8-row ones)
-        while (sg > 8 && (long long)c->cm_gx * ((ny + sg - 1) / sg) * batch < 6 * 148) sg /= 2;
+        // (tools/seg_sweep.py, 8 chains: 1024^2 - 32 rows 6340, 64 rows 7170, 128 rows 7100 chain-steps/s; 2048^2 x 2 -
+        // 32 rows 1755, 64 rows 1840, 128 rows 1725: four blocks per SM are enough, halo rows cost more than the tail)
+        while (sg > 8 && (long long)c->cm_gx * ((ny + sg - 1) / sg) * batch < 4 * 148) sg /= 2;
         if (sg == 8 && (long long)c->cm_gx * ((ny + 7) / 8) * batch < 2 * 148) sg = 4;      // less than two blocks per SM
         // very large batches (64 chains at 4096^2): longer segments cut the share of the vertical halo rows; only while
         // the grid still has >= 20 waves of 3 blocks per SM, so that the tail wave stays negligible (4096^2 x 64 chains:
