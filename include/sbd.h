@@ -280,6 +280,9 @@ const char* sbd_phase_name(int i);
  *   "chamb_coop"   the whole prox (all sweeps, stop test, f) as ONE cooperative launch, one warp per (row, 64-pixel
  *                  strip), blocks of an image synchronised by a barrier per sweep (tv_coop.cuh): 1 whenever the grid
  *                  fits the device, 0 never, -1 automatic (rows*cols*chains <= 2^21 and none of the options above set)
+ *   "overlap"      0: launch the prox of a SAPG iteration on the main stream (serial order) instead of on its own
+ *                  stream next to the statistics / scalar update / next gradient (same results either way)
+ *   "pdl"          0: launch the fused Chambolle kernels without programmatic dependent launch
  *   "tv_seg"       rows per segment of the TVnorm / single-sweep / output kernels
  *   "geom_chains"  derive the geometry from this many chains instead of the batch
  * sbd_get_geometry: out = {levels, chamb_seg, chamb_grid_x, chamb_grid_y,

@@ -12,6 +12,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HDR = os.path.join(ROOT, "include", "sbd.h")
+PKG = "semi-blind-image-deblurring-problems-with-tv_b200"
 
 
 @pytest.fixture(scope="module")
@@ -132,3 +133,25 @@ def test_make_params_follows_the_reference_constants(built):
     p = H.make_params(H.LAPLACE, l)
     assert (p.c_theta, p.c_psi[0], p.c_sigma2) == (0.01, 100.0, 10000.0)                # laplace.m:139-141
     assert p.chambolle_maxiter == 25 and p.chambolle_tol == 1e-3 and p.chambolle_tau == 0.249
+
+
+def test_every_option_is_documented():
+    """Each name sbd_set_option accepts is described in include/sbd.h and (the tuning ones) in DESIGN.md's knob table;
+    SBD_N_GEOM agrees between the header, the ctypes mirror and the geometry keys of host.py."""
+    import re
+    src = open(os.path.join(ROOT, PKG, "csrc", "sbd.cu")).read()
+    body = src[src.index("int sbd_set_option("):]
+    body = body[:body.index("int sbd_get_geometry(")]
+    names = re.findall(r'n == "(\w+)"', body)
+    assert len(names) >= 9 and "chamb_coop" in names
+    header = open(os.path.join(ROOT, "include", "sbd.h")).read()
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    for n in names:
+        assert f'"{n}"' in header, n
+        assert f'"{n}"' in design, n
+    ngeom = int(re.search(r"#define SBD_N_GEOM (\d+)", header).group(1))
+    lib_py = open(os.path.join(ROOT, PKG, "_lib.py")).read()
+    assert int(re.search(r"SBD_N_GEOM = (\d+)", lib_py).group(1)) == ngeom
+    host_py = open(os.path.join(ROOT, PKG, "host.py")).read()
+    keys = re.search(r"keys = \(([^)]*)\)", host_py).group(1)
+    assert len(re.findall(r'"\w+"', keys)) == ngeom
